@@ -1,0 +1,369 @@
+// api.cu -- the C ABI (include/stp_rasterizer.h): stage sequencing and arena carve-up.
+//
+// Replaces: CudaRasterizer::Rasterizer::{forward,backward,markVisible} (rasterizer_impl.cu:161-173,
+// 221-413, 417-526) and the json -> SplattingSettings conversion (rasterizer.h:160-182).
+// Everything is enqueued on the caller's stream; the only host<->device synchronisation is the
+// read-back of num_rendered that sizes the binning arena (the reference blocks in the same place,
+// rasterizer_impl.cu:317).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/stp_rasterizer.h"
+#include "stp_kernels.cuh"
+
+using namespace stp;
+
+namespace {
+
+thread_local std::string g_error;
+thread_local std::vector<std::pair<const char*, float>> g_timings;
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_error = std::string("CUDA error in ") + where + ": " + cudaGetErrorString(e);
+    return STP_ERR_CUDA;
+}
+
+#define STP_CUDA(call, where)                             \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+        if (debug & 1) {                                  \
+            e__ = cudaStreamSynchronize(stream);          \
+            if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+        }                                                 \
+    } while (0)
+
+bool convert_settings(const StpSettings* in, Settings& s, std::string& err, bool backward) {
+    if (in == nullptr) {
+        err = "settings must not be NULL";
+        return false;
+    }
+    if (in->sort_mode < 0 || in->sort_mode > 3) {
+        err = "invalid sort_mode";
+        return false;
+    }
+    if (in->sort_order < 0 || in->sort_order > 3) {
+        err = "invalid sort_order";
+        return false;
+    }
+    s.sort_mode = in->sort_mode;
+    s.sort_order = in->sort_order;
+    s.q_mid = in->queue_tile_2x2;
+    s.q_head = in->queue_per_pixel;
+    s.rect_bounding = in->rect_bounding != 0;
+    s.tight_opacity_bounding = in->tight_opacity_bounding != 0;
+    s.tile_based_culling = in->tile_based_culling != 0;
+    s.hier_culling = in->hierarchical_4x4_culling != 0;
+    s.proper_ewa_scaling = in->proper_ewa_scaling != 0;
+    if (s.sort_mode == STP_SORT_HIER) {
+        // instantiated queue sizes, forward.cu:445-480 / backward.cu:739-767
+        if (s.q_mid != 8 && s.q_mid != 12 && s.q_mid != 20) {
+            err = "Not supported mid queue size " + std::to_string(s.q_mid);
+            return false;
+        }
+        const bool head_ok = s.q_head == 4 || s.q_head == 8 || s.q_head == 16 || (backward && s.q_head == 12);
+        if (!head_ok) {
+            err = "Not supported head queue size " + std::to_string(s.q_head);
+            return false;
+        }
+    }
+    return true;
+}
+
+Frame make_frame(const float* background, int W, int H, const StpTileBand* band, const float* viewmatrix,
+                 const float* projmatrix, const float* inv_viewproj, const float* cam_pos, float tan_fovx,
+                 float tan_fovy) {
+    Frame f;
+    f.viewmatrix = viewmatrix;
+    f.projmatrix = projmatrix;
+    f.inv_viewproj = inv_viewproj;
+    f.cam_pos = cam_pos;
+    f.background = background;
+    f.W = W;
+    f.H = H;
+    f.grid_x = (W + 15) / 16;
+    f.grid_y = (H + 15) / 16;
+    f.row0 = 0;
+    f.row1 = f.grid_y;
+    if (band != nullptr && band->row_end >= 0) {
+        f.row0 = band->row_begin < 0 ? 0 : (band->row_begin > f.grid_y ? f.grid_y : band->row_begin);
+        f.row1 = band->row_end > f.grid_y ? f.grid_y : band->row_end;
+        if (f.row1 < f.row0) f.row1 = f.row0;
+    }
+    f.tan_fovx = tan_fovx;
+    f.tan_fovy = tan_fovy;
+    // rasterizer_impl.cu:251-252
+    f.focal_y = H / (2.0f * tan_fovy);
+    f.focal_x = W / (2.0f * tan_fovx);
+    return f;
+}
+
+struct StageTimer {
+    bool on;
+    cudaStream_t stream;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    StageTimer(bool on_, cudaStream_t s) : on(on_), stream(s) { mark(nullptr); }
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        ev.push_back(e);
+        names.push_back(name);
+    }
+    void finish() {
+        if (!on) return;
+        cudaEventSynchronize(ev.back());
+        g_timings.clear();
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            g_timings.push_back({names[i], ms});
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* stp_last_error(void) { return g_error.c_str(); }
+int stp_abi_version(void) { return STP_ABI_VERSION; }
+
+int stp_last_timings(float* ms, const char** names, int max_n) {
+    int n = 0;
+    for (auto& t : g_timings) {
+        if (n >= max_n) break;
+        ms[n] = t.second;
+        names[n] = t.first;
+        ++n;
+    }
+    return n;
+}
+
+int stp_requires_cov3D_inv(const StpSettings* s) {
+    if (s == nullptr) return 0;
+    return s->sort_mode != STP_SORT_GLOBAL || s->sort_order == STP_ORDER_PTD_CENTER || s->sort_order == STP_ORDER_PTD_MAX;
+}
+
+size_t stp_geometry_bytes(int P, int inv) { return required<GeometryState>((size_t)P, inv != 0); }
+size_t stp_binning_bytes(int R) { return required<BinningState>((size_t)R, sort_temp_bytes((size_t)R)); }
+size_t stp_image_bytes(int W, int H) {
+    return required<ImageState>((size_t)W * H, (size_t)((W + 15) / 16) * ((H + 15) / 16));
+}
+
+int stp_view_geometry(char* buf, int P, int inv, StpGeometryView* out) {
+    if (buf == nullptr || out == nullptr) return fail(STP_ERR_INVALID_ARGUMENT, "null argument");
+    char* p = buf;
+    GeometryState g = GeometryState::from_chunk(p, (size_t)P, inv != 0);
+    out->depths = g.depths;
+    out->clamped = g.clamped;
+    out->rects2D = reinterpret_cast<float*>(g.rects2D);
+    out->means2D = reinterpret_cast<float*>(g.means2D);
+    out->cov3D = g.cov3D;
+    out->cov3D_inv = reinterpret_cast<float*>(g.cov3D_inv);
+    out->conic_opacity = reinterpret_cast<float*>(g.conic_opacity);
+    out->rgb = g.rgb;
+    out->tiles_touched = g.tiles_touched;
+    out->point_offsets = g.point_offsets;
+    return STP_OK;
+}
+int stp_view_binning(char* buf, int R, StpBinningView* out) {
+    if (buf == nullptr || out == nullptr) return fail(STP_ERR_INVALID_ARGUMENT, "null argument");
+    char* p = buf;
+    BinningState b = BinningState::from_chunk(p, (size_t)R, 0);
+    out->point_list = b.point_list;
+    out->point_list_keys = b.keys;
+    return STP_OK;
+}
+int stp_view_image(char* buf, int W, int H, StpImageView* out) {
+    if (buf == nullptr || out == nullptr) return fail(STP_ERR_INVALID_ARGUMENT, "null argument");
+    char* p = buf;
+    ImageState s = ImageState::from_chunk(p, (size_t)W * H, (size_t)((W + 15) / 16) * ((H + 15) / 16));
+    out->final_T = s.final_T;
+    out->n_contrib = s.n_contrib;
+    out->ranges = reinterpret_cast<uint32_t*>(s.ranges);
+    return STP_OK;
+}
+
+int stp_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* /*projmatrix*/,
+                     uint8_t* present, void* stream_) {
+    if (P <= 0) return STP_OK;
+    cudaError_t e = launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream_);
+    if (e != cudaSuccess) return cuda_fail(e, "mark_visible");
+    return STP_OK;
+}
+
+int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_alloc, void* binning_user,
+                stp_alloc_fn image_alloc, void* image_user, int P, int D, int M, const float* background, int width,
+                int height, const StpSettings* settings, const StpTileBand* band, const float* means3D, const float* shs,
+                const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                const float* inv_viewprojmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
+                float* out_color, int* radii, int debug, void* stream_, int* num_rendered_out) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (num_rendered_out) *num_rendered_out = 0;
+    Settings s;
+    std::string err;
+    if (!convert_settings(settings, s, err, false)) return fail(STP_ERR_UNSUPPORTED, err);
+    if (P <= 0) return STP_OK;  // rasterize_points.cu:93
+    if (!geom_alloc || !binning_alloc || !image_alloc) return fail(STP_ERR_INVALID_ARGUMENT, "allocator callbacks required");
+    if (shs == nullptr && colors_precomp == nullptr)
+        return fail(STP_ERR_INVALID_ARGUMENT, "For non-RGB, provide precomputed Gaussian colors!");
+    if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
+        return fail(STP_ERR_INVALID_ARGUMENT, "provide scales+rotations or cov3D_precomp");
+    if (s.requires_inv() && (scales == nullptr || rotations == nullptr))
+        return fail(STP_ERR_INVALID_ARGUMENT, "depth-along-ray sort modes need scales and rotations (forward.cu:208-211)");
+    if (s.sort_mode == STP_SORT_PPX_FULL || s.sort_mode == STP_SORT_PPX_KBUFFER)
+        return fail(STP_ERR_UNSUPPORTED, "sort mode not built yet in this round (PPX_FULL / PPX_KBUFFER)");
+
+    Frame f = make_frame(background, width, height, band, viewmatrix, projmatrix, inv_viewprojmatrix, cam_pos, tan_fovx,
+                         tan_fovy);
+    const int tiles = f.grid_x * f.grid_y;
+    const bool inv = s.requires_inv();
+    StageTimer timer((debug & 2) != 0, stream);
+
+    char* gp = geom_alloc(geom_user, required<GeometryState>((size_t)P, inv));
+    if (!gp) return fail(STP_ERR_ALLOC, "geometry arena allocation failed");
+    GeometryState g = GeometryState::from_chunk(gp, (size_t)P, inv);
+    char* ip = image_alloc(image_user, required<ImageState>((size_t)width * height, (size_t)tiles));
+    if (!ip) return fail(STP_ERR_ALLOC, "image arena allocation failed");
+    ImageState img = ImageState::from_chunk(ip, (size_t)width * height, (size_t)tiles);
+
+    PreprocessArgs pa;
+    pa.P = P; pa.D = D; pa.M = M;
+    pa.means3D = means3D; pa.scales = scales; pa.rotations = rotations; pa.opacities = opacities;
+    pa.shs = shs; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
+    pa.scale_modifier = scale_modifier;
+    pa.sort_order = s.sort_order;
+    pa.rect_bounding = s.rect_bounding;
+    pa.tight_opacity_bounding = s.tight_opacity_bounding;
+    pa.proper_ewa_scaling = s.proper_ewa_scaling;
+    pa.prefiltered = prefiltered != 0;
+    pa.radii = radii;
+    STP_CUDA(launch_preprocess(pa, f, g, s.tile_based_culling, stream), "preprocess");
+    timer.mark("Preprocess");
+
+    uint32_t R = 0;
+    {
+        cudaError_t e = cudaMemcpyAsync(&R, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "num_rendered read-back");
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return cuda_fail(e, "num_rendered read-back");
+    }
+    if (num_rendered_out) *num_rendered_out = (int)R;
+
+    const size_t sort_bytes = sort_temp_bytes((size_t)R);
+    char* bp = binning_alloc(binning_user, required<BinningState>((size_t)R, sort_bytes));
+    if (!bp) return fail(STP_ERR_ALLOC, "binning arena allocation failed");
+    BinningState b = BinningState::from_chunk(bp, (size_t)R, sort_bytes);
+
+    if (R > 0) {
+        STP_CUDA(launch_duplicate(P, f, s, g, radii, b.keys_unsorted, b.point_list_unsorted, stream), "duplicate");
+    }
+    timer.mark("Duplicate");
+    const int bit = (int)higher_msb((uint32_t)tiles);
+    STP_CUDA(launch_sort(b, (size_t)R, 32 + bit, stream), "sort");
+    STP_CUDA(launch_tile_ranges((size_t)R, b.keys, img.ranges, tiles, stream), "tile ranges");
+    timer.mark("Sort");
+
+    RenderArgs ra;
+    ra.ranges = img.ranges;
+    ra.point_list = b.point_list;
+    ra.means2D = g.means2D;
+    ra.conic_opacity = g.conic_opacity;
+    ra.cov3D_inv = g.cov3D_inv;
+    ra.colors = colors_precomp != nullptr ? colors_precomp : g.rgb;
+    ra.final_T = img.final_T;
+    ra.n_contrib = img.n_contrib;
+    ra.out_color = out_color;
+    if (s.sort_mode == STP_SORT_GLOBAL) {
+        STP_CUDA(launch_render_global_fwd(f, ra, stream), "render (GLOBAL)");
+    } else {
+        STP_CUDA(launch_render_hier_fwd(f, s, ra, stream), "render (HIER)");
+    }
+    timer.mark("Render");
+    timer.finish();
+    return STP_OK;
+}
+
+int stp_backward(int P, int D, int M, int R, const float* background, int width, int height, const StpSettings* settings,
+                 const StpTileBand* band, const float* means3D, const float* shs, const float* opacities,
+                 const float* colors_precomp, const float* scales, float scale_modifier, const float* rotations,
+                 const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                 const float* inv_viewprojmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                 const float* pixel_colors, const int* radii, char* geom_buffer, char* binning_buffer,
+                 char* image_buffer, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                 float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                 int debug, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Settings s;
+    std::string err;
+    if (!convert_settings(settings, s, err, true)) return fail(STP_ERR_UNSUPPORTED, err);
+    if (P <= 0) return STP_OK;  // rasterize_points.cu:191
+    if (s.sort_mode == STP_SORT_PPX_FULL)
+        return fail(STP_ERR_UNSUPPORTED, "Backward not supported for full per-pixel sort");  // backward.cu:735
+    if (s.sort_mode == STP_SORT_PPX_KBUFFER) return fail(STP_ERR_UNSUPPORTED, "PPX_KBUFFER not built yet in this round");
+    if (!geom_buffer || !binning_buffer || !image_buffer) return fail(STP_ERR_INVALID_ARGUMENT, "null arena");
+
+    Frame f = make_frame(background, width, height, band, viewmatrix, projmatrix, inv_viewprojmatrix, cam_pos, tan_fovx,
+                         tan_fovy);
+    const int tiles = f.grid_x * f.grid_y;
+    const bool inv = s.requires_inv();
+    StageTimer timer((debug & 2) != 0, stream);
+    char* gp = geom_buffer;
+    GeometryState g = GeometryState::from_chunk(gp, (size_t)P, inv);
+    char* bp = binning_buffer;
+    BinningState b = BinningState::from_chunk(bp, (size_t)R, 0);
+    char* ip = image_buffer;
+    ImageState img = ImageState::from_chunk(ip, (size_t)width * height, (size_t)tiles);
+
+    RenderBwdArgs ra;
+    ra.ranges = img.ranges;
+    ra.point_list = b.point_list;
+    ra.means2D = g.means2D;
+    ra.conic_opacity = g.conic_opacity;
+    ra.cov3D_inv = g.cov3D_inv;
+    ra.colors = colors_precomp != nullptr ? colors_precomp : g.rgb;
+    ra.final_T = img.final_T;
+    ra.n_contrib = img.n_contrib;
+    ra.pixel_colors = pixel_colors;
+    ra.dL_dpix = dL_dpix;
+    ra.dL_dmean2D = dL_dmean2D;
+    ra.dL_dconic = dL_dconic;
+    ra.dL_dopacity = dL_dopacity;
+    ra.dL_dcolor = dL_dcolor;
+    if (R > 0) {
+        if (s.sort_mode == STP_SORT_GLOBAL) {
+            STP_CUDA(launch_render_global_bwd(f, ra, stream), "render backward (GLOBAL)");
+        } else {
+            STP_CUDA(launch_render_hier_bwd(f, s, ra, stream), "render backward (HIER)");
+        }
+    }
+    timer.mark("RenderBackward");
+
+    PreprocessBwdArgs pa;
+    pa.P = P; pa.D = D; pa.M = M;
+    pa.means3D = means3D; pa.radii = radii; pa.shs = shs; pa.clamped = g.clamped; pa.opacities = opacities;
+    pa.scales = scales; pa.rotations = rotations; pa.scale_modifier = scale_modifier;
+    pa.cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
+    pa.proper_ewa_scaling = s.proper_ewa_scaling;
+    pa.dL_dmean2D = dL_dmean2D; pa.dL_dconic = dL_dconic; pa.dL_dopacity = dL_dopacity;
+    pa.dL_dmean3D = dL_dmean3D; pa.dL_dcolor = dL_dcolor; pa.dL_dcov3D = dL_dcov3D; pa.dL_dsh = dL_dsh;
+    pa.dL_dscale = dL_dscale; pa.dL_drot = dL_drot;
+    STP_CUDA(launch_preprocess_bwd(pa, f, stream), "preprocess backward");
+    timer.mark("PreprocessBackward");
+    timer.finish();
+    return STP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+// preprocess.cu -- per-Gaussian projection, culling, tile counting, SH->RGB and the offset scan,
+// fused in ONE kernel.
+//
+// Replaces: preprocessCUDA<3,TBC,LB> (forward.cu:68-229) + cub::DeviceScan::InclusiveSum
+// (rasterizer_impl.cu:313) + checkFrustum (rasterizer_impl.cu:113-128).
+//
+// B200 design notes
+//   * one thread per Gaussian, 256-thread CTAs, grid sized by P (memory-bound: ~236 B in, ~90-140 B out
+//     per Gaussian); CTAs take a dynamic ticket so the single-pass decoupled-look-back scan can never
+//     dead-lock and point_offsets come out in Gaussian-index order (needed for the stable tie order of
+//     the sort: equal (tile,depth) keys stay in ascending Gaussian index, like the reference).
+//   * SH coefficients (192 of the 236 input bytes) are only read for survivors and are pulled
+//     warp-cooperatively: the 32 lanes stream one survivor's contiguous 12*M bytes with coalesced
+//     loads into shared memory (row stride M*3+1 -> conflict-free), instead of 48 strided scalar
+//     loads per thread.
+//   * the exact-tile-count loop of tile_based_culling is always load balanced: the first
+//     kSeqTiles tiles of a rectangle are tested by the owning thread, the remainder by the whole warp.
+//     Results do not depend on the schedule (settings.load_balancing is a no-op by construction).
+#include "stp_kernels.cuh"
+
+namespace stp {
+
+namespace {
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+__constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                               -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                               -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+constexpr int kSeqTiles = 8;  // tiles of a rectangle tested sequentially by the owner thread
+
+// SH -> RGB (computeColorFromSH, forward_common.h:20-70); sh points at this Gaussian's
+// coefficients in shared memory, stride 3 floats per coefficient.
+__device__ __forceinline__ void eval_sh(int deg, const float* __restrict__ sh, float dx, float dy, float dz,
+                                        float* __restrict__ rgb, uint8_t* __restrict__ clamped3) {
+    const float len = fsqrt(ffma(dz, dz, ffma(dx, dx, fmul(dy, dy))));
+    const float x = fdiv(dx, len), y = fdiv(dy, len), z = fdiv(dz, len);
+    float r[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = SH_C0 * sh[c];
+    if (deg > 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r[c] = r[c] - SH_C1 * y * sh[3 + c] + SH_C1 * z * sh[6 + c] - SH_C1 * x * sh[9 + c];
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                r[c] = r[c] + SH_C2[0] * xy * sh[12 + c] + SH_C2[1] * yz * sh[15 + c] +
+                       SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + SH_C2[3] * xz * sh[21 + c] +
+                       SH_C2[4] * (xx - yy) * sh[24 + c];
+            if (deg > 2) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    r[c] = r[c] + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] + SH_C3[1] * xy * z * sh[30 + c] +
+                           SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
+                           SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
+                           SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] + SH_C3[5] * z * (xx - yy) * sh[42 + c] +
+                           SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        r[c] += 0.5f;
+        clamped3[c] = (r[c] < 0.0f) ? 1 : 0;
+        rgb[c] = fmaxf(r[c], 0.0f);
+    }
+}
+
+// does tile (tx,ty) pass the exact contribution test? (computeTilebasedCullingTileCount,
+// stopthepop_common.cuh:176-262; same arithmetic in duplicateWithKeys_extended :419-452)
+__device__ __forceinline__ bool tile_contributes(float A, float B, float C, float2 xy, float thr, int tx, int ty) {
+    float mx, my;
+    const float p = max_contrib_power<15, 15>(A, B, C, xy.x, xy.y, (float)(tx * 16), (float)(ty * 16),
+                                              (float)(tx * 16 + 15), (float)(ty * 16 + 15), mx, my);
+    return p <= thr;
+}
+
+}  // namespace
+
+template <bool TBC>
+__global__ void __launch_bounds__(kPreprocessThreads)
+preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g) {
+    extern __shared__ float s_sh[];  // [8 warps][32 rows][sh_stride]
+    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_warp_sum[kPreprocessThreads / 32];
+    __shared__ uint32_t s_prefix;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(&g.counters[0], 1u);
+    __syncthreads();
+    const uint32_t bid = s_ticket;
+    const int idx = bid * kPreprocessThreads + tid;
+    const bool valid = idx < a.P;
+
+    bool alive = valid;
+    uint32_t tiles = 0;
+    float x = 0.f, y = 0.f, z = 0.f;
+    Vec3 pv{0.f, 0.f, 1.f};
+    float4 co = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 mean2D = make_float2(0.f, 0.f), rect_ext = make_float2(0.f, 0.f);
+    float radius = 0.f, thr = 0.f;
+    TileRect rc{0, 0, 0, 0};
+
+    if (valid) {
+        x = a.means3D[3 * idx + 0];
+        y = a.means3D[3 * idx + 1];
+        z = a.means3D[3 * idx + 2];
+        pv = view_transform(f.viewmatrix, x, y, z);
+        if (pv.z <= kNearPlane) {  // in_frustum, auxiliary.h:223
+            alive = false;
+            if (a.prefiltered) atomicOr(&g.counters[2], 1u);
+        }
+    }
+
+    float cov6[6];
+    if (alive) {
+        if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cov6[k] = a.cov3D_precomp[6 * idx + k];
+        } else {
+            const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+            const Rot3 R = quat_to_rot(q.x, q.y, q.z, q.w);
+            const float sx = a.scales[3 * idx + 0], sy = a.scales[3 * idx + 1], sz = a.scales[3 * idx + 2];
+            gram_scaled_rot(R, fmul(a.scale_modifier, sx), fmul(a.scale_modifier, sy), fmul(a.scale_modifier, sz), cov6);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) g.cov3D[6 * idx + k] = cov6[k];
+        }
+        const Vec3 cov = project_cov2d(pv, f.focal_x, f.focal_y, f.tan_fovx, f.tan_fovy, cov6, f.viewmatrix);
+        // dilateCov2D + computeConicOpacity, forward_common.h:108-144
+        const float ca = fadd(cov.x, 0.3f), cc = fadd(cov.z, 0.3f), cb = cov.y;
+        const float bb = fmul(cb, cb);
+        const float det = ffma(ca, cc, -bb);
+        float scaling = 1.0f;
+        if (a.proper_ewa_scaling) {
+            const float det_orig = ffma(cov.x, cov.z, -bb);
+            scaling = fsqrt(fmaxf(0.000025f, fdiv(det_orig, det)));
+        }
+        if (det == 0.0f) {
+            alive = false;
+        } else {
+            const float det_inv = fdiv(1.0f, det);
+            co.x = fmul(cc, det_inv);
+            co.y = fmul(cb, -det_inv);
+            co.z = fmul(ca, det_inv);
+            co.w = fmul(a.opacities[idx], scaling);
+            if (co.w < kAlphaThreshold) alive = false;
+        }
+        if (alive) {
+            thr = logf(fdiv(co.w, kAlphaThreshold));
+            float extent = 3.33f;
+            if (a.tight_opacity_bounding) extent = (float)fmin(3.33, (double)fsqrt(fadd(thr, thr)));
+            const float mid = fmul(0.5f, fadd(ca, cc));
+            const float lambda = fadd(mid, fsqrt(fmaxf(0.01f, ffma(mid, mid, -det))));
+            radius = fmul(extent, fsqrt(lambda));
+            if (radius <= 0.0f) alive = false;
+            if (alive) {
+                mean2D = project_mean2d(f.projmatrix, x, y, z, f.W, f.H);
+                rect_ext.x = fminf(a.rect_bounding ? fmul(extent, fsqrt(ca)) : radius, radius);
+                rect_ext.y = fminf(a.rect_bounding ? fmul(extent, fsqrt(cc)) : radius, radius);
+                rc = tile_rect(mean2D, rect_ext, f.grid_x, f.grid_y, f.row0, f.row1);
+                tiles = (uint32_t)((rc.x1 - rc.x0) * (rc.y1 - rc.y0));
+                if (tiles == 0) alive = false;
+            }
+        }
+    }
+
+    if constexpr (TBC) {
+        // exact tile count: owner thread tests the first kSeqTiles tiles, the warp shares the rest
+        const int rect_tiles = alive ? (int)tiles : 0;
+        const int rw = max(rc.x1 - rc.x0, 1);
+        int count = 0;
+        for (int t = 0; t < min(rect_tiles, kSeqTiles); ++t)
+            count += tile_contributes(co.x, co.y, co.z, mean2D, thr, rc.x0 + t % rw, rc.y0 + t / rw) ? 1 : 0;
+        uint32_t big = __ballot_sync(0xffffffffu, rect_tiles > kSeqTiles);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const float A = __shfl_sync(0xffffffffu, co.x, src), B = __shfl_sync(0xffffffffu, co.y, src),
+                        C = __shfl_sync(0xffffffffu, co.z, src);
+            const float2 m = make_float2(__shfl_sync(0xffffffffu, mean2D.x, src), __shfl_sync(0xffffffffu, mean2D.y, src));
+            const float th = __shfl_sync(0xffffffffu, thr, src);
+            const int x0 = __shfl_sync(0xffffffffu, rc.x0, src), y0 = __shfl_sync(0xffffffffu, rc.y0, src);
+            const int w = __shfl_sync(0xffffffffu, rw, src), n = __shfl_sync(0xffffffffu, rect_tiles, src);
+            int c = 0;
+            for (int t = kSeqTiles + lane; t < n; t += 32) c += tile_contributes(A, B, C, m, th, x0 + t % w, y0 + t / w) ? 1 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == src) count += c;
+        }
+        if (alive) {
+            tiles = (uint32_t)count;
+            if (tiles == 0) alive = false;
+        }
+    }
+    if (!alive) tiles = 0;
+
+    // ---- survivors: colour, inverse covariance, stores --------------------------------------
+    if (a.colors_precomp == nullptr && a.M > 0) {
+        const int stride = a.M * 3 + 1;
+        float* my_rows = s_sh + (size_t)warp * 32 * stride;
+        uint32_t surv = __ballot_sync(0xffffffffu, alive);
+        const int warp_base = (int)bid * kPreprocessThreads + warp * 32;
+        const int n_sh = a.M * 3;
+        while (surv) {
+            const int r = __ffs(surv) - 1;
+            surv &= surv - 1;
+            const float* __restrict__ src = a.shs + (size_t)(warp_base + r) * n_sh;
+            for (int k = lane; k < n_sh; k += 32) my_rows[r * stride + k] = __ldg(src + k);
+        }
+        __syncwarp();
+        if (alive) {
+            float rgb[3];
+            uint8_t cl[3];
+            eval_sh(a.D, my_rows + lane * stride, fsub(x, f.cam_pos[0]), fsub(y, f.cam_pos[1]), fsub(z, f.cam_pos[2]),
+                    rgb, cl);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                g.rgb[3 * idx + c] = rgb[c];
+                g.clamped[3 * idx + c] = cl[c];
+            }
+        }
+    }
+
+    if (alive) {
+        const float vx = fsub(f.cam_pos[0], x), vy = fsub(f.cam_pos[1], y), vz = fsub(f.cam_pos[2], z);
+        if (g.cov3D_inv != nullptr) {
+            // computeInvCov3D + packing, stopthepop_common.cuh:13-41, forward.cu:208-220
+            const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+            const Rot3 R = quat_to_rot(q.x, q.y, q.z, q.w);
+            const float sx = a.scales[3 * idx + 0], sy = a.scales[3 * idx + 1], sz = a.scales[3 * idx + 2];
+            float ic[6];
+            gram_scaled_rot(R, fdiv(1.0f, fmul(a.scale_modifier, fmaxf(1e-3f, sx))),
+                            fdiv(1.0f, fmul(a.scale_modifier, fmaxf(1e-3f, sy))),
+                            fdiv(1.0f, fmul(a.scale_modifier, fmaxf(1e-3f, sz))), ic);
+            const float ux = ffma(-ic[2], vz, ffma(-ic[1], vy, -fmul(ic[0], vx)));
+            const float uy = ffma(-ic[4], vz, ffma(-ic[3], vy, -fmul(ic[1], vx)));
+            const float uz = ffma(-ic[5], vz, ffma(-ic[4], vy, -fmul(ic[2], vx)));
+            g.cov3D_inv[3 * idx + 0] = make_float4(ic[0], ic[1], ic[2], 0.f);
+            g.cov3D_inv[3 * idx + 1] = make_float4(ic[3], ic[4], ic[5], 0.f);
+            g.cov3D_inv[3 * idx + 2] = make_float4(ux, uy, uz, 0.f);
+        }
+        g.depths[idx] = (a.sort_order == 0) ? pv.z : fsqrt(ffma(vz, vz, ffma(vx, vx, fmul(vy, vy))));
+        g.rects2D[idx] = rect_ext;
+        g.means2D[idx] = mean2D;
+        g.conic_opacity[idx] = co;
+    }
+    if (valid) {
+        a.radii[idx] = alive ? (int)ceilf(radius) : 0;
+        g.tiles_touched[idx] = tiles;
+    }
+
+    // ---- inclusive scan of tiles over the whole grid (decoupled look-back) --------------------
+    uint32_t incl = tiles;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPreprocessThreads / 32; ++w) {
+        const uint32_t v = s_warp_sum[w];
+        if (w < warp) warp_off += v;
+        block_total += v;
+    }
+    if (warp == 0) {
+        constexpr unsigned long long FLAG_AGG = 1ull << 32, FLAG_INC = 2ull << 32;
+        volatile unsigned long long* st = g.scan_state;
+        uint32_t excl = 0;
+        if (bid == 0) {
+            if (lane == 0) st[0] = FLAG_INC | block_total;
+        } else {
+            if (lane == 0) st[bid] = FLAG_AGG | block_total;
+            int look = (int)bid - 1;
+            while (true) {
+                const int j = look - lane;
+                unsigned long long v = (j >= 0) ? st[j] : FLAG_INC;
+                while (__any_sync(0xffffffffu, (v >> 32) == 0)) v = (j >= 0) ? st[j] : FLAG_INC;
+                const uint32_t inc_mask = __ballot_sync(0xffffffffu, (v >> 32) == 2);
+                // lanes before (and including) the first inclusive flag contribute
+                const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+                uint32_t c = (lane <= first_inc) ? (uint32_t)(v & 0xffffffffull) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                __threadfence();
+                st[bid] = FLAG_INC | (unsigned long long)(excl + block_total);
+            }
+        }
+        if (lane == 0) {
+            s_prefix = excl;
+            if (bid == gridDim.x - 1) g.counters[1] = excl + block_total;  // R
+        }
+    }
+    __syncthreads();
+    if (valid) g.point_offsets[idx] = s_prefix + warp_off + incl;
+}
+
+// markVisible (rasterizer_impl.cu:113-128): the same near-plane test, nothing else.
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ vm,
+                                    uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const Vec3 pv = view_transform(vm, means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    present[idx] = !(pv.z <= kNearPlane);
+}
+
+cudaError_t launch_preprocess(const PreprocessArgs& a, const Frame& f, const GeometryState& g, bool tbc,
+                              cudaStream_t stream) {
+    const int blocks = (a.P + kPreprocessThreads - 1) / kPreprocessThreads;
+    cudaError_t e = cudaMemsetAsync(g.scan_state, 0, sizeof(unsigned long long) * blocks, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * 64, stream);
+    if (e != cudaSuccess) return e;
+    const size_t smem = (a.colors_precomp == nullptr && a.M > 0) ? sizeof(float) * 8 * 32 * (a.M * 3 + 1) : 0;
+    if (tbc) {
+        cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        preprocess_kernel<true><<<blocks, kPreprocessThreads, smem, stream>>>(a, f, g);
+    } else {
+        cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        preprocess_kernel<false><<<blocks, kPreprocessThreads, smem, stream>>>(a, f, g);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t stream) {
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, vm, present);
+    return cudaGetLastError();
+}
+
+}  // namespace stp

@@ -1,0 +1,121 @@
+// stp_state.cuh -- arena layouts (HBM data layout of the fwd->bwd scratch) and kernel argument packs.
+//
+// The three arenas play the role of the reference's GeometryState / BinningState / ImageState
+// (rasterizer_impl.h:29-67, carve-up rasterizer_impl.cu:175-217): opaque byte buffers owned by the
+// caller, re-derived from the same pointer in backward.  Sub-arrays are carved sequentially, each
+// aligned to 256 B so that float4 / 128-bit accesses and TMA bulk copies (16 B granularity) are
+// always legal.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace stp {
+
+constexpr size_t kArenaAlign = 256;
+constexpr int kPreprocessThreads = 256;
+
+template <typename T>
+static inline void obtain(char*& chunk, T*& ptr, size_t count) {
+    size_t off = (reinterpret_cast<uintptr_t>(chunk) + kArenaAlign - 1) & ~(kArenaAlign - 1);
+    ptr = reinterpret_cast<T*>(off);
+    chunk = reinterpret_cast<char*>(ptr + count);
+}
+
+// per-Gaussian scratch: 87 B (+48 B with inverse covariance) like the reference, plus the
+// decoupled-look-back scan state (8 B per 256 Gaussians) that replaces the CUB scan temp.
+struct GeometryState {
+    float* depths;
+    uint8_t* clamped;
+    float2* rects2D;
+    float2* means2D;
+    float* cov3D;
+    float4* cov3D_inv;  // nullptr unless requiresDepthAlongRay
+    float4* conic_opacity;
+    float* rgb;
+    uint32_t* tiles_touched;
+    uint32_t* point_offsets;
+    unsigned long long* scan_state;  // [ceil(P/256)] (flag<<32 | value)
+    uint32_t* counters;              // [0] dynamic CTA ticket, [1] R (total instances), [2] error flags
+
+    static GeometryState from_chunk(char*& chunk, size_t P, bool inv) {
+        GeometryState g;
+        obtain(chunk, g.depths, P);
+        obtain(chunk, g.clamped, P * 3);
+        obtain(chunk, g.rects2D, P);
+        obtain(chunk, g.means2D, P);
+        obtain(chunk, g.cov3D, P * 6);
+        g.cov3D_inv = nullptr;
+        if (inv) obtain(chunk, g.cov3D_inv, P * 3);
+        obtain(chunk, g.conic_opacity, P);
+        obtain(chunk, g.rgb, P * 3);
+        obtain(chunk, g.tiles_touched, P);
+        obtain(chunk, g.point_offsets, P);
+        obtain(chunk, g.scan_state, (P + kPreprocessThreads - 1) / kPreprocessThreads);
+        obtain(chunk, g.counters, 64);
+        return g;
+    }
+};
+
+struct ImageState {
+    float* final_T;
+    uint32_t* n_contrib;
+    uint2* ranges;
+    static ImageState from_chunk(char*& chunk, size_t N, size_t tiles) {
+        ImageState s;
+        obtain(chunk, s.final_T, N);
+        obtain(chunk, s.n_contrib, N);
+        obtain(chunk, s.ranges, tiles);
+        return s;
+    }
+};
+
+struct BinningState {
+    uint32_t* point_list;
+    uint32_t* point_list_unsorted;
+    uint64_t* keys;
+    uint64_t* keys_unsorted;
+    char* sort_space;
+    size_t sort_bytes;
+    static BinningState from_chunk(char*& chunk, size_t R, size_t sort_bytes) {
+        BinningState b;
+        obtain(chunk, b.point_list, R);
+        obtain(chunk, b.point_list_unsorted, R);
+        obtain(chunk, b.keys, R);
+        obtain(chunk, b.keys_unsorted, R);
+        obtain(chunk, b.sort_space, sort_bytes);
+        b.sort_bytes = sort_bytes;
+        return b;
+    }
+};
+
+template <typename T, typename... A>
+static inline size_t required(A... a) {
+    char* p = nullptr;
+    T::from_chunk(p, a...);
+    return reinterpret_cast<size_t>(p) + kArenaAlign;
+}
+
+// camera / frame constants, passed by value (lives in the constant bank of every kernel)
+struct Frame {
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* inv_viewproj;
+    const float* cam_pos;
+    const float* background;
+    int W, H;
+    int grid_x, grid_y;
+    int row0, row1;  // tile-row band [row0,row1); whole image = [0,grid_y)
+    float tan_fovx, tan_fovy;
+    float focal_x, focal_y;
+};
+
+struct Settings {
+    int sort_mode, sort_order;
+    int q_mid, q_head;
+    bool rect_bounding, tight_opacity_bounding, tile_based_culling, hier_culling, proper_ewa_scaling;
+    bool per_tile_depth() const { return sort_order == 2 || sort_order == 3; }
+    bool requires_inv() const { return sort_mode != 0 || per_tile_depth(); }
+};
+
+}  // namespace stp

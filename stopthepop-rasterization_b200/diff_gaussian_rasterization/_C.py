@@ -1,0 +1,289 @@
+"""ctypes binding of libstp_rasterizer.so with the call surface of the reference's pybind module.
+
+Mirrors ``diff_gaussian_rasterization._C`` of r4dl/StopThePop-Rasterization (ext.cpp:15-19):
+
+    rasterize_gaussians(...22 positional args...)  -> (num_rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer)
+    rasterize_gaussians_backward(...25 args...)    -> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+    mark_visible(means3D, viewmatrix, projmatrix)  -> bool[P]
+
+(signatures: rasterize_points.h:26-82; tensor allocation and marshalling: rasterize_points.cu:43-253).
+PyTorch is used for device memory and the current stream only; all compute happens in the hand
+written sm_100a kernels behind the C ABI declared in include/stp_rasterizer.h.  There is no CPU or
+eager fallback: a missing library is an ImportError.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.environ.get("STP_RASTERIZER_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libstp_rasterizer.so"))
+
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        f"{_LIB_PATH} not found: build the CUDA library first "
+        "(python -c 'import __graft_entry__ as g; g.build()' or python stopthepop-rasterization_b200/csrc/build.py). "
+        "There is no CPU fallback for the rasterizer.")
+
+_lib = ctypes.CDLL(_LIB_PATH)
+
+NUM_CHANNELS = 3  # config.h:15
+
+
+class StpSettings(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "sort_mode", "sort_order", "queue_tile_4x4", "queue_tile_2x2", "queue_per_pixel", "rect_bounding",
+        "tight_opacity_bounding", "tile_based_culling", "hierarchical_4x4_culling", "load_balancing",
+        "proper_ewa_scaling")]
+
+
+class StpTileBand(ctypes.Structure):
+    _fields_ = [("row_begin", ctypes.c_int32), ("row_end", ctypes.c_int32)]
+
+
+class StpGeometryView(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "depths", "clamped", "rects2D", "means2D", "cov3D", "cov3D_inv", "conic_opacity", "rgb", "tiles_touched",
+        "point_offsets")]
+
+
+class StpBinningView(ctypes.Structure):
+    _fields_ = [("point_list", ctypes.c_void_p), ("point_list_keys", ctypes.c_void_p)]
+
+
+class StpImageView(ctypes.Structure):
+    _fields_ = [("final_T", ctypes.c_void_p), ("n_contrib", ctypes.c_void_p), ("ranges", ctypes.c_void_p)]
+
+
+ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+_P = ctypes.c_void_p
+_lib.stp_last_error.restype = ctypes.c_char_p
+_lib.stp_abi_version.restype = ctypes.c_int
+_lib.stp_geometry_bytes.restype = ctypes.c_size_t
+_lib.stp_geometry_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+_lib.stp_binning_bytes.restype = ctypes.c_size_t
+_lib.stp_binning_bytes.argtypes = [ctypes.c_int]
+_lib.stp_image_bytes.restype = ctypes.c_size_t
+_lib.stp_image_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+_lib.stp_requires_cov3D_inv.argtypes = [ctypes.POINTER(StpSettings)]
+_lib.stp_view_geometry.argtypes = [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(StpGeometryView)]
+_lib.stp_view_binning.argtypes = [_P, ctypes.c_int, ctypes.POINTER(StpBinningView)]
+_lib.stp_view_image.argtypes = [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(StpImageView)]
+_lib.stp_mark_visible.argtypes = [ctypes.c_int, _P, _P, _P, _P, _P]
+_lib.stp_last_timings.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_char_p), ctypes.c_int]
+_lib.stp_forward.restype = ctypes.c_int
+_lib.stp_forward.argtypes = [
+    ALLOC_FN, _P, ALLOC_FN, _P, ALLOC_FN, _P,  # arenas
+    ctypes.c_int, ctypes.c_int, ctypes.c_int,  # P D M
+    _P, ctypes.c_int, ctypes.c_int,            # background W H
+    ctypes.POINTER(StpSettings), ctypes.POINTER(StpTileBand),
+    _P, _P, _P, _P, _P, ctypes.c_float, _P, _P,  # means3D shs colors opac scales mod rot cov3D
+    _P, _P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_int,  # view proj inv campos tanx tany prefiltered
+    _P, _P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_int)]  # out_color radii debug stream num_rendered
+_lib.stp_backward.restype = ctypes.c_int
+_lib.stp_backward.argtypes = [
+    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,  # P D M R
+    _P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(StpSettings), ctypes.POINTER(StpTileBand),
+    _P, _P, _P, _P, _P, ctypes.c_float, _P, _P,  # means3D shs opac colors scales mod rot cov3D
+    _P, _P, _P, _P, ctypes.c_float, ctypes.c_float,  # view proj inv campos tanx tany
+    _P, _P, _P, _P, _P, _P,  # pixel_colors radii geom binning image dL_dpix
+    _P, _P, _P, _P, _P, _P, _P, _P, _P,  # 9 grads
+    ctypes.c_int, _P]
+
+if _lib.stp_abi_version() != 1:
+    raise ImportError("libstp_rasterizer.so ABI version mismatch")
+
+LIBRARY_PATH = _LIB_PATH
+
+
+def _err():
+    return _lib.stp_last_error().decode("utf-8", "replace")
+
+
+def settings_from_dict(d):
+    """dict produced by ExtendedSettings.to_dict() -> StpSettings; every key mandatory like the
+    reference's from_json (rasterizer.h:160-182 uses .at())."""
+    ss, cs = d["sort_settings"], d["culling_settings"]
+    q = ss["queue_sizes"]
+    return StpSettings(int(ss["sort_mode"]), int(ss["sort_order"]), int(q["tile_4x4"]), int(q["tile_2x2"]),
+                       int(q["per_pixel"]), int(bool(cs["rect_bounding"])), int(bool(cs["tight_opacity_bounding"])),
+                       int(bool(cs["tile_based_culling"])), int(bool(cs["hierarchical_4x4_culling"])),
+                       int(bool(d["load_balancing"])), int(bool(d["proper_ewa_scaling"])))
+
+
+def _ptr(t):
+    """device pointer of a tensor, or NULL for the reference's 'absent' convention (empty tensor)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32(t, device):
+    if t is None or t.numel() == 0:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("expected a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError("expected a float32 tensor")
+    return t.contiguous()
+
+
+class _Arena:
+    """one resizable byte buffer handed to the library as an allocation callback
+    (resizeFunctional, rasterize_points.cu:33-41)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, nbytes):
+        try:
+            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            return self.tensor.data_ptr()
+        except Exception:  # out of memory -> NULL, reported by the library as STP_ERR_ALLOC
+            return None
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
+                        degree, campos, prefiltered, settings_dict, render_depth, debug, tile_band=None):
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:68-71
+    if render_depth:
+        raise RuntimeError("render_depth (debug visualisation) is outside the B200 hot path; see DESIGN.md")
+    device = means3D.device
+    P, H, W = means3D.size(0), int(image_height), int(image_width)
+    out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+    radii = torch.zeros((P,), dtype=torch.int32, device=device)
+    geom, binning, img = _Arena(device), _Arena(device), _Arena(device)
+    st = settings_from_dict(settings_dict)
+    if P == 0:
+        return 0, out_color, radii, geom.tensor, binning.tensor, img.tensor
+    means3D = _f32(means3D, device)
+    keep = [_f32(t, device) for t in (background, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix,
+                                      projmatrix, inv_viewprojmatrix, sh, campos)]
+    background, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, sh, campos = keep
+    M = sh.size(1) if sh is not None and sh.size(0) != 0 else 0
+    band = ctypes.byref(StpTileBand(int(tile_band[0]), int(tile_band[1]))) if tile_band is not None else None
+    n = ctypes.c_int(0)
+    with torch.cuda.device(device):
+        rc = _lib.stp_forward(geom.cb, None, binning.cb, None, img.cb, None, P, int(degree), M, _ptr(background), W, H,
+                              ctypes.byref(st), band, _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity),
+                              _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                              _ptr(viewmatrix), _ptr(projmatrix), _ptr(inv_viewprojmatrix), _ptr(campos),
+                              float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), out_color.data_ptr(),
+                              radii.data_ptr(), int(debug) if not isinstance(debug, bool) else int(debug),
+                              _stream(device), ctypes.byref(n))
+    if rc != 0:
+        raise RuntimeError(_err())
+    return n.value, out_color, radii, geom.tensor, binning.tensor, img.tensor
+
+
+def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, scales, rotations, scale_modifier,
+                                 cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy,
+                                 pixel_colors, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                 imageBuffer, settings_dict, debug, tile_band=None):
+    device = means3D.device
+    P = means3D.size(0)
+    H, W = dL_dout_color.size(1), dL_dout_color.size(2)  # rasterize_points.cu:169-170
+    M = sh.size(1) if sh is not None and sh.numel() != 0 else 0
+    st = settings_from_dict(settings_dict)
+    # one zero-filled slab instead of nine torch::zeros (rasterize_points.cu:178-186)
+    widths = [3, 3, 3, 4, 1, 6, 3 * M, 3, 4]  # means3D means2D colors conic opacity cov3D sh scales rot
+    flat = torch.zeros((sum(widths) * P,), dtype=torch.float32, device=device)
+    views, off = [], 0
+    for w in widths:
+        views.append(flat[off:off + w * P])
+        off += w * P
+    dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dconic, dL_dopacity, dL_dcov3D, dL_dsh, dL_dscales, dL_drot = views
+    if P != 0:
+        means3D = _f32(means3D, device)
+        keep = [_f32(t, device) for t in (background, opacities, colors, scales, rotations, cov3D_precomp, viewmatrix,
+                                          projmatrix, inv_viewprojmatrix, pixel_colors, dL_dout_color, sh, campos)]
+        (background, opacities, colors, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix,
+         pixel_colors, dL_dout_color, sh, campos) = keep
+        radii = radii.contiguous()
+        band = ctypes.byref(StpTileBand(int(tile_band[0]), int(tile_band[1]))) if tile_band is not None else None
+        with torch.cuda.device(device):
+            rc = _lib.stp_backward(P, int(degree), M, int(R), _ptr(background), W, H, ctypes.byref(st), band,
+                                   _ptr(means3D), _ptr(sh), _ptr(opacities), _ptr(colors), _ptr(scales),
+                                   float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
+                                   _ptr(projmatrix), _ptr(inv_viewprojmatrix), _ptr(campos), float(tan_fovx),
+                                   float(tan_fovy), _ptr(pixel_colors), _ptr(radii), _ptr(geomBuffer),
+                                   _ptr(binningBuffer), _ptr(imageBuffer), _ptr(dL_dout_color), _ptr(dL_dmeans2D),
+                                   _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D),
+                                   _ptr(dL_dcov3D), _ptr(dL_dsh) if M else None, _ptr(dL_dscales), _ptr(dL_drot),
+                                   int(debug), _stream(device))
+        if rc != 0:
+            raise RuntimeError(_err())
+    return (dL_dmeans2D.view(P, 3), dL_dcolors.view(P, NUM_CHANNELS), dL_dopacity.view(P, 1), dL_dmeans3D.view(P, 3),
+            dL_dcov3D.view(P, 6), dL_dsh.view(P, M, 3), dL_dscales.view(P, 3), dL_drot.view(P, 4))
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    P = means3D.size(0)
+    present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+    if P != 0:
+        m, v, p = means3D.contiguous(), viewmatrix.contiguous(), projmatrix.contiguous()
+        with torch.cuda.device(means3D.device):
+            rc = _lib.stp_mark_visible(P, m.data_ptr(), v.data_ptr(), p.data_ptr(), present.data_ptr(),
+                                       _stream(means3D.device))
+        if rc != 0:
+            raise RuntimeError(_err())
+    return present
+
+
+# ---- decoders of the opaque arenas, for the parity tests -----------------------------------------
+def _wrap(ptr, owner, count, dtype):
+    """torch view of `count` elements at device address `ptr` inside the uint8 tensor `owner`."""
+    if not ptr:
+        return None
+    off = ptr - owner.data_ptr()
+    nbytes = count * torch.empty((), dtype=dtype).element_size()
+    return owner[off:off + nbytes].view(dtype)
+
+
+def view_geometry(geomBuffer, P, settings_dict):
+    st = settings_from_dict(settings_dict)
+    inv = _lib.stp_requires_cov3D_inv(ctypes.byref(st))
+    v = StpGeometryView()
+    _lib.stp_view_geometry(geomBuffer.data_ptr(), P, inv, ctypes.byref(v))
+    f32, u8, u32 = torch.float32, torch.uint8, torch.int32
+    return dict(depths=_wrap(v.depths, geomBuffer, P, f32), clamped=_wrap(v.clamped, geomBuffer, 3 * P, u8).view(P, 3),
+                rects2D=_wrap(v.rects2D, geomBuffer, 2 * P, f32).view(P, 2),
+                means2D=_wrap(v.means2D, geomBuffer, 2 * P, f32).view(P, 2),
+                cov3D=_wrap(v.cov3D, geomBuffer, 6 * P, f32).view(P, 6),
+                cov3D_inv=(_wrap(v.cov3D_inv, geomBuffer, 12 * P, f32).view(P, 3, 4) if v.cov3D_inv else None),
+                conic_opacity=_wrap(v.conic_opacity, geomBuffer, 4 * P, f32).view(P, 4),
+                rgb=_wrap(v.rgb, geomBuffer, 3 * P, f32).view(P, 3),
+                tiles_touched=_wrap(v.tiles_touched, geomBuffer, P, u32),
+                point_offsets=_wrap(v.point_offsets, geomBuffer, P, u32))
+
+
+def view_binning(binningBuffer, R):
+    v = StpBinningView()
+    _lib.stp_view_binning(binningBuffer.data_ptr(), R, ctypes.byref(v))
+    return dict(point_list=_wrap(v.point_list, binningBuffer, R, torch.int32),
+                point_list_keys=_wrap(v.point_list_keys, binningBuffer, R, torch.int64))
+
+
+def view_image(imgBuffer, W, H):
+    v = StpImageView()
+    _lib.stp_view_image(imgBuffer.data_ptr(), W, H, ctypes.byref(v))
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    return dict(final_T=_wrap(v.final_T, imgBuffer, W * H, torch.float32).view(H, W),
+                n_contrib=_wrap(v.n_contrib, imgBuffer, W * H, torch.int32).view(H, W),
+                ranges=_wrap(v.ranges, imgBuffer, 2 * tiles, torch.int32).view(tiles, 2))
+
+
+def last_timings():
+    ms = (ctypes.c_float * 16)()
+    names = (ctypes.c_char_p * 16)()
+    n = _lib.stp_last_timings(ms, names, 16)
+    return [(names[i].decode(), ms[i]) for i in range(n)]

@@ -1,0 +1,290 @@
+"""Drop-in ``diff_gaussian_rasterization`` for the StopThePop training loop, backed by the B200-native
+CUDA library (libstp_rasterizer.so, sm_100a).
+
+Public surface = the reference's Python package (diff_gaussian_rasterization/__init__.py of
+r4dl/StopThePop-Rasterization): same names, field order, defaults, argument meaning and exceptions.
+
+    GaussianRasterizationSettings  (NamedTuple, __init__.py:248-263)
+    GaussianRasterizer             (nn.Module,  __init__.py:265-314)
+    rasterize_gaussians / _RasterizeGaussians (autograd.Function, __init__.py:32-172)
+    SortMode, GlobalSortOrder      (IntEnum,    __init__.py:175-191)
+    SortQueueSizes, SortSettings, CullingSettings, ExtendedSettings (dataclasses, __init__.py:193-246)
+
+Differences that are deliberate and invisible to callers: dataclass defaults use default_factory
+(the reference's mutable defaults do not import on Python >= 3.11), ``ExtendedSettings.from_dict``
+does not need ``dacite``, and the native module is a ctypes binding of a C ABI instead of pybind11.
+"""
+import json
+from dataclasses import asdict, dataclass, field
+from enum import IntEnum
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _C
+
+
+def enum_dict_factory(data):
+    def convert_value(obj):
+        if isinstance(obj, IntEnum):
+            return obj.value
+        return obj
+    return dict((k, convert_value(v)) for k, v in data)
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    copied_tensors = [item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple]
+    return tuple(copied_tensors)
+
+
+def rasterize_gaussians(
+    means3D,
+    means2D,
+    sh,
+    colors_precomp,
+    opacities,
+    scales,
+    rotations,
+    cov3Ds_precomp,
+    raster_settings,
+):
+    return _RasterizeGaussians.apply(
+        means3D,
+        means2D,
+        sh,
+        colors_precomp,
+        opacities,
+        scales,
+        rotations,
+        cov3Ds_precomp,
+        raster_settings,
+    )
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """autograd glue; argument packing follows __init__.py:70-93 (forward) and :122-158 (backward)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        rs = raster_settings
+        args = (
+            rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+            rs.viewmatrix, rs.projmatrix, rs.inv_viewprojmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+            rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.settings.to_dict(), rs.render_depth,
+            rs.debug,
+        )
+        if rs.debug:
+            cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
+            try:
+                num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
+
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(colors_precomp, means3D, opacities, scales, rotations, cov3Ds_precomp, radii, sh, color,
+                              geomBuffer, binningBuffer, imgBuffer)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _):
+        num_rendered = ctx.num_rendered
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, opacities, scales, rotations, cov3Ds_precomp, radii, sh, color, geomBuffer,
+         binningBuffer, imgBuffer) = ctx.saved_tensors
+        args = (rs.bg, means3D, radii, opacities, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                rs.viewmatrix, rs.projmatrix, rs.inv_viewprojmatrix, rs.tanfovx, rs.tanfovy, color, grad_out_color, sh,
+                rs.sh_degree, rs.campos, geomBuffer, num_rendered, binningBuffer, imgBuffer, rs.settings.to_dict(),
+                rs.debug)
+        if rs.debug:
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                grads8 = _C.rasterize_gaussians_backward(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            grads8 = _C.rasterize_gaussians_backward(*args)
+        (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
+         grad_rotations) = grads8
+        return (
+            grad_means3D,
+            grad_means2D,
+            grad_sh,
+            grad_colors_precomp,
+            grad_opacities,
+            grad_scales,
+            grad_rotations,
+            grad_cov3Ds_precomp,
+            None,
+        )
+
+
+class SortMode(IntEnum):
+    GLOBAL = 0
+    PPX_FULL = 1
+    PPX_KBUFFER = 2
+    HIER = 3
+
+    def __str__(self):
+        return self.name
+
+
+class GlobalSortOrder(IntEnum):
+    Z_DEPTH = 0
+    DISTANCE = 1
+    PTD_CENTER = 2
+    PTD_MAX = 3
+
+    def __str__(self):
+        return self.name
+
+
+@dataclass
+class SortQueueSizes:
+    tile_4x4: int = 64
+    tile_2x2: int = 8
+    per_pixel: int = 4
+
+    def set_value(self, key, value):
+        if key in self.__dataclass_fields__.keys():
+            self.__setattr__(key, value)
+
+
+@dataclass
+class SortSettings:
+    queue_sizes: SortQueueSizes = field(default_factory=SortQueueSizes)
+    sort_mode: SortMode = SortMode.GLOBAL
+    sort_order: GlobalSortOrder = GlobalSortOrder.Z_DEPTH
+
+    def set_value(self, key, value):
+        if key in self.__dataclass_fields__.keys():
+            self.__setattr__(key, value)
+        else:
+            self.queue_sizes.set_value(key, value)
+
+
+@dataclass
+class CullingSettings:
+    rect_bounding: bool = False
+    tight_opacity_bounding: bool = False
+    tile_based_culling: bool = False
+    hierarchical_4x4_culling: bool = False
+
+    def set_value(self, key, value):
+        if key in self.__dataclass_fields__.keys():
+            self.__setattr__(key, value)
+
+
+@dataclass
+class ExtendedSettings:
+    sort_settings: SortSettings = field(default_factory=SortSettings)
+    culling_settings: CullingSettings = field(default_factory=CullingSettings)
+    load_balancing: bool = False
+    proper_ewa_scaling: bool = False
+
+    def to_dict(self):
+        return asdict(self, dict_factory=enum_dict_factory)
+
+    def to_json(self):
+        return json.dumps(self.to_dict())
+
+    @staticmethod
+    def from_dict(dict):
+        # what dacite.from_dict(..., Config(cast=[IntEnum])) does in the reference (__init__.py:236-237):
+        # missing keys fall back to the dataclass defaults, ints are cast to the enums.
+        d = dict
+        ss = d.get("sort_settings", {})
+        q = ss.get("queue_sizes", {})
+        cs = d.get("culling_settings", {})
+        qd, sd, cd, ed = SortQueueSizes(), SortSettings(), CullingSettings(), ExtendedSettings()
+        return ExtendedSettings(
+            sort_settings=SortSettings(
+                queue_sizes=SortQueueSizes(tile_4x4=int(q.get("tile_4x4", qd.tile_4x4)),
+                                           tile_2x2=int(q.get("tile_2x2", qd.tile_2x2)),
+                                           per_pixel=int(q.get("per_pixel", qd.per_pixel))),
+                sort_mode=SortMode(ss.get("sort_mode", sd.sort_mode)),
+                sort_order=GlobalSortOrder(ss.get("sort_order", sd.sort_order))),
+            culling_settings=CullingSettings(
+                rect_bounding=bool(cs.get("rect_bounding", cd.rect_bounding)),
+                tight_opacity_bounding=bool(cs.get("tight_opacity_bounding", cd.tight_opacity_bounding)),
+                tile_based_culling=bool(cs.get("tile_based_culling", cd.tile_based_culling)),
+                hierarchical_4x4_culling=bool(cs.get("hierarchical_4x4_culling", cd.hierarchical_4x4_culling))),
+            load_balancing=bool(d.get("load_balancing", ed.load_balancing)),
+            proper_ewa_scaling=bool(d.get("proper_ewa_scaling", ed.proper_ewa_scaling)))
+
+    @staticmethod
+    def from_json(json_filename):
+        return ExtendedSettings.from_dict(json.load(open(json_filename)))
+
+    def set_value(self, key, value):
+        if key in self.__dataclass_fields__.keys():
+            self.__setattr__(key, value)
+        else:
+            self.culling_settings.set_value(key, value)
+            self.sort_settings.set_value(key, value)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    inv_viewprojmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    settings: ExtendedSettings
+    render_depth: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        # Mark visible points (based on frustum culling for camera) with a boolean
+        with torch.no_grad():
+            raster_settings = self.raster_settings
+            visible = _C.mark_visible(positions, raster_settings.viewmatrix, raster_settings.projmatrix)
+        return visible
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+
+        # Invoke the CUDA rasterization routine
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   raster_settings)
