@@ -78,8 +78,10 @@ def make_camera(W, H, yaw=0.0):
     return Camera(H, W, float(tanfovx), float(tanfovy), view, proj, inv, campos, bg), R, t
 
 
-def make_scene(P, W, H, seed):
-    """P Gaussians distributed through (and a little outside) the frustum of make_camera(W, H)."""
+def make_scene(P, W, H, seed, sigma_scale=None):
+    """P Gaussians distributed through (and a little outside) the frustum of make_camera(W, H).
+    sigma_scale overrides the pixel-footprint factor H/1080 (used by the small golden fixtures to get
+    long per-tile lists on tiny images)."""
     g = torch.Generator().manual_seed(seed)
     cam, R, t = make_camera(W, H)
     focal = 0.9 * W
@@ -92,7 +94,7 @@ def make_scene(P, W, H, seed):
     y = z * cam.tanfovy * U(-1.15, 1.15, P)
     p_cam = torch.stack([x, y, z], dim=1).double()
     means3D = ((p_cam - t) @ R).float().contiguous()  # R^T (p - t), row-vector form
-    sigma_px = torch.exp(U(math.log(0.4), math.log(6.0), P)) * (H / 1080.0)
+    sigma_px = torch.exp(U(math.log(0.4), math.log(6.0), P)) * (H / 1080.0 if sigma_scale is None else sigma_scale)
     scales = (sigma_px * z.abs() / focal).unsqueeze(1) * torch.exp(U(math.log(0.3), 0.0, P, 3))
     scales = scales.clamp_min(1e-7).contiguous()
     q = torch.randn(P, 4, generator=g, dtype=torch.float32)
