@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: sorted-Gaussian rasterizer forward + backward (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3a|C3b|C1]
+
+A "step" is one fwd+bwd pass of the rasterizer over one view of the synthetic cloud of SURVEY 8(d).
+N=1 workload = BASELINE.json configs[1]: 1M Gaussians, 1920x1080, GLOBAL sort mode, fwd+bwd.
+N>1: view sharding (SURVEY 8e / north_star "or batched views"): every rank holds the same Gaussians and
+renders its own camera (yaw = rank * 0.08 rad), then ONE NCCL all-reduce(sum) of the flat parameter-gradient
+slab -- the data-parallel training step; per-GPU work is fixed => "scaling": "weak".
+
+Printed JSON line (rank 0):
+  value     Mpixels/s, whole job, Gaussians + camera + upstream gradient resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the public autograd API (GaussianRasterizer) with the step's inputs (camera
+            matrices + upstream-gradient image) copied from pinned HOST memory and the rendered image read back
+            to the host inside the timed region.  The Gaussian parameters are the model state and stay resident.
+            `e2e_full_upload` additionally uploads every Gaussian parameter and downloads every gradient.
+  roofline  dominant kernel: algorithmic bytes (SURVEY 8d formula at the measured P,V,R) / CUDA-event time of
+            that kernel averaged over the timed steps (stage events recorded inside the library, resolved lazily)
+  cpu_baseline  the plain-C oracle port (OpenMP, all host cores) on a bounded sample, N=1 only
+--impl reference: the reference's own implementation.  The reference ships NO CPU path, so this
+arm times the UNMODIFIED reference CUDA build (oracle/_ref, compiled from /root/reference for sm_100) on the same
+GPU through its own _C API, same workload, same copies; if oracle/_ref is absent it falls back to the C oracle port.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "stopthepop-rasterization_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import stp_scenes as S  # noqa: E402
+
+WORKLOADS = {
+    # name: (scene config, settings overrides, description)
+    "C1": ("C1", dict(), "C1: 1k Gaussians, 256x256, GLOBAL"),
+    "C2": ("C2", dict(), "C2: 1M Gaussians, 1920x1080, GLOBAL tile sort, fwd+bwd (BASELINE.json configs[1])"),
+    "C3a": ("C3", dict(sort_mode=3), "C3a: 4M Gaussians, 1920x1080, HIER 64/8/4, fwd+bwd"),
+    "C3b": ("C3", dict(S.STOPTHEPOP_PRESET), "C3b: 4M Gaussians, 1920x1080, StopThePop preset, fwd+bwd"),
+}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(P, V, R, N, T, M, s_flag, c_flag):
+    """SURVEY.md 8(d) per-stage algorithmic bytes (fixed formula, measured P,V,R)."""
+    passes = 6
+    return {
+        "Preprocess": 12 * P + V * (12 + 16 + 4 + 12 * M) + 8 * P + V * (4 + 8 + 8 + 24 + 16 + 12 + 3 + 48 * c_flag) + 8 * P,
+        "Duplicate": 8 * P + 20 * V + 12 * R,
+        "Sort": passes * 24 * R + 8 * R + 8 * R + 16 * T,
+        "Render": 8 * T + R * (28 + 48 * s_flag) + 12 * V + 20 * N,
+        "RenderBackward": 8 * T + R * (40 + 48 * s_flag) + N * (20 + 12 * s_flag) + 72 * V,
+        "PreprocessBackward": 4 * P + 88 * V + 4 * P + V * (103 + 12 * M) + V * (40 + 12 * M),
+    }
+
+
+KERNEL_OF_STAGE = {"Preprocess": "preprocess_kernel", "Duplicate": "duplicate_kernel", "Sort": "radix sort + tile_ranges_kernel",
+                   "Render": "render_*_fwd_kernel", "RenderBackward": "render_*_bwd_kernel",
+                   "PreprocessBackward": "preprocess_bwd_kernel"}
+
+
+def event_time_ms(fn, steps, warmup, world):
+    """W untimed warm-ups, then exactly K steps bracketed by barrier + synchronize; max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, repeats):
+    from oracle import cpu_oracle as co
+    args = [t.numpy() for t in (sc_c.means3D, sc_c.scales, sc_c.rotations, sc_c.opacities, sc_c.shs)]
+    cargs = [t.numpy() for t in (cam_c.viewmatrix, cam_c.projmatrix, cam_c.inv_viewprojmatrix, cam_c.campos, cam_c.bg)]
+    co.lib()
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        o = co.Oracle(settings, *args, sc_c.sh_degree, *cargs, cam_c.tanfovx, cam_c.tanfovy, cam_c.image_width,
+                      cam_c.image_height)
+        o.backward(dL_c.numpy())
+        o.close()
+    return (time.perf_counter() - t0) / repeats
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    scene_name, overrides, desc = WORKLOADS[a.workload]
+    settings = S.default_settings_dict(**overrides)
+    cid, P, W, H = S.CONFIGS[scene_name]
+    pixels = W * H
+
+    from oracle import ref_api as ref
+    use_ref_gpu = a.impl == "reference" and ref.available() and torch.cuda.is_available()
+
+    if a.impl == "reference" and not use_ref_gpu:
+        # no reference CUDA build travelled with the repo: the C oracle port on the host cores
+        if rank != 0:
+            return
+        sc_c, cam_c = S.make_config(scene_name)
+        dL_c = S.make_upstream_grad(W, H, 2000 + cid)
+        for _ in range(1):
+            cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, 1)
+        sec = cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, max(1, min(a.steps, 3)))
+        v = pixels / sec / 1e6
+        print(json.dumps({"impl": "reference", "metric": "Mpixels/s fwd+bwd", "value": v, "unit": "Mpixels/s",
+                          "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": desc},
+                          "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "port",
+                                           "sample": "full workload, oracle/stp_oracle.c with OpenMP"},
+                          "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: same Gaussians on every rank, one camera per rank ---------------------------------------
+    sc_c, cam0_c = S.make_config(scene_name)
+    cam_c, _, _ = S.make_camera(W, H, yaw=0.08 * rank)
+    dL_c = S.make_upstream_grad(W, H, 2000 + cid + rank)
+    sc, cam = S.to_device(sc_c, dev), S.to_device(cam_c, dev)
+    dL = dL_c.to(dev)
+    e = torch.empty(0, device=dev)
+    M = sc.shs.shape[1]
+
+    if a.impl == "ours":
+        from diff_gaussian_rasterization import (ExtendedSettings, GaussianRasterizationSettings, GaussianRasterizer, _C)
+
+        def fwd(c, dbg=2):
+            return _C.rasterize_gaussians(c.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e,
+                                          c.viewmatrix, c.projmatrix, c.inv_viewprojmatrix, c.tanfovx, c.tanfovy, H, W,
+                                          sc.shs, sc.sh_degree, c.campos, False, settings, False, dbg)
+
+        def bwd(c, out, g, dbg=2):
+            return _C.rasterize_gaussians_backward(c.bg, sc.means3D, out[2], sc.opacities, e, sc.scales, sc.rotations,
+                                                   1.0, e, c.viewmatrix, c.projmatrix, c.inv_viewprojmatrix, c.tanfovx,
+                                                   c.tanfovy, out[1], g, sc.shs, sc.sh_degree, c.campos, out[3], out[0],
+                                                   out[4], out[5], settings, dbg, want_param_slab=True)
+    else:
+        def fwd(c, dbg=False):
+            return ref.forward(sc, c, settings)
+
+        def bwd(c, out, g, dbg=False):
+            grads = ref.backward(sc, c, settings, out, g)
+            return grads, grads  # the reference returns 8 separate tensors
+
+    state = {}
+
+    def step_resident():
+        out = fwd(cam)
+        grads, slab = bwd(cam, out, dL)
+        if world > 1:
+            if a.impl == "ours":
+                dist.all_reduce(slab)
+            else:
+                for t in (slab[3], slab[5], slab[2], slab[6], slab[7]):
+                    dist.all_reduce(t)
+        state["out"], state["grads"] = out, grads
+
+    # ---- e2e: public API, per-step host inputs -------------------------------------------------------------
+    pin = lambda t: t.clone().pin_memory()  # noqa: E731
+    h_cam = [pin(t) for t in (cam_c.viewmatrix, cam_c.projmatrix, cam_c.inv_viewprojmatrix, cam_c.campos, cam_c.bg)]
+    h_dL = pin(dL_c)
+    h_img = torch.empty(3, H, W, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * 4 for t in h_cam) + h_dL.numel() * 4
+    d2h = h_img.numel() * 4
+    leaves = [t.clone().requires_grad_(True) for t in (sc.means3D, sc.opacities, sc.shs, sc.scales, sc.rotations)]
+    means2D = torch.zeros_like(sc.means3D, requires_grad=True)
+
+    def step_e2e():
+        vm, pm, iv, cp, bg = [t.to(dev, non_blocking=True) for t in h_cam]
+        g = h_dL.to(dev, non_blocking=True)
+        for t in leaves + [means2D]:
+            t.grad = None
+        m3, op, sh, scl, rot = leaves
+        if a.impl == "ours":
+            rs = GaussianRasterizationSettings(H, W, cam_c.tanfovx, cam_c.tanfovy, bg, 1.0, vm, pm, iv, sc.sh_degree, cp,
+                                               False, ext_settings, False, False)
+            color, radii = GaussianRasterizer(rs)(m3, means2D, op, shs=sh, scales=scl, rotations=rot)
+            color.backward(g)
+            if world > 1:
+                for t in leaves:
+                    dist.all_reduce(t.grad)
+        else:
+            c = cam._replace(viewmatrix=vm, projmatrix=pm, inv_viewprojmatrix=iv, campos=cp, bg=bg)
+            out = ref.forward(sc, c, settings)
+            grads = ref.backward(sc, c, settings, out, g)
+            color = out[1]
+            if world > 1:
+                for t in (grads[3], grads[5], grads[2], grads[6], grads[7]):
+                    dist.all_reduce(t)
+        h_img.copy_(color.detach(), non_blocking=True)
+
+    if a.impl == "ours":
+        ext_settings = ExtendedSettings.from_dict(settings)
+
+    # full-upload variant: every Gaussian parameter host->device, every parameter gradient device->host
+    h_params = [pin(t) for t in (sc_c.means3D, sc_c.opacities, sc_c.shs, sc_c.scales, sc_c.rotations)]
+    h_grads = [torch.empty_like(t).pin_memory() for t in h_params]
+    h2d_full = h2d + sum(t.numel() * 4 for t in h_params)
+    d2h_full = d2h + sum(t.numel() * 4 for t in h_grads)
+
+    def step_e2e_full():
+        nonlocal leaves
+        leaves = [t.to(dev, non_blocking=True).requires_grad_(True) for t in h_params]
+        step_e2e()
+        if a.impl == "ours":
+            for hg, t in zip(h_grads, leaves):
+                hg.copy_(t.grad, non_blocking=True)
+
+    # ---- timed regions --------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if a.impl == "ours":
+        _C.timing_reset()
+        for _ in range(a.warmup):
+            step_resident()
+        torch.cuda.synchronize()
+        _C.timing_reset()
+        launches0 = _C.kernel_launches()
+    if rank == 0:
+        sampler.start()
+    ms_total = event_time_ms(step_resident, a.steps, a.warmup if a.impl != "ours" else 0, world)
+    if a.impl == "ours":
+        launches = _C.kernel_launches() - launches0
+        stages = _C.timing_summary()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / a.steps
+    value = world * pixels / (ms_step * 1e-3) / 1e6
+
+    ms_e2e = event_time_ms(step_e2e, a.steps, a.warmup, world) / a.steps
+    e2e_value = world * pixels / (ms_e2e * 1e-3) / 1e6
+    e2e_full = None
+    if a.impl == "ours" and world == 1:
+        ms_full = event_time_ms(step_e2e_full, max(3, a.steps // 4), 3, world) / max(3, a.steps // 4)
+        e2e_full = {"value": pixels / (ms_full * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d_full,
+                    "d2h_bytes_per_step": d2h_full}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    out = state["out"]
+    R = int(out[0])
+    V = int((out[2] > 0).sum().item())
+    line = {
+        "metric": "Mpixels/s fwd+bwd", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "P": P, "W": W, "H": H, "visible": V, "num_rendered": R,
+                   "sharding": "views (one camera per rank, replicated Gaussians, NCCL all-reduce of parameter grads)"
+                   if world > 1 else "single GPU",
+                   "l2_policy": "inputs larger than L2 (236 B/Gaussian x P + instance lists >> 126 MB)" if P >= 10**6
+                   else "small parity config; L2-resident"},
+        "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e,
+                "what": "GaussianRasterizer autograd API; camera + upstream-gradient image from pinned host memory, "
+                        "rendered image read back; Gaussian parameters (model state) resident"},
+        "clocks": clocks,
+    }
+    if a.impl == "ours":
+        N, T = pixels, ((W + 15) // 16) * ((H + 15) // 16)
+        s_flag = 0 if settings["sort_settings"]["sort_mode"] == 0 else 1
+        c_flag = 1 if (s_flag or settings["sort_settings"]["sort_order"] in (2, 3)) else 0
+        ab = algorithmic_bytes(P, V, R, N, T, M, s_flag, c_flag)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        per_stage = {k: {"ms": v[0], "GBps": ab[k] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None, "bytes": ab[k]}
+                     for k, v in stages.items() if k in ab}
+        own = {k: v for k, v in per_stage.items() if k != "Sort"}  # the sort is a library call (CUB) in this round
+        dom = max(own, key=lambda k: own[k]["ms"])
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(a.workload, {}).get(dom)
+        except Exception:
+            pass
+        line["roofline"] = {"bound": "hbm", "kernel": KERNEL_OF_STAGE[dom], "stage": dom,
+                            "achieved": per_stage[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                            "frac": per_stage[dom]["GBps"] / peak, "traffic": traffic,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                            "algorithmic_bytes": ab[dom], "kernel_ms": per_stage[dom]["ms"],
+                            "stages": per_stage,
+                            "whole_step": {"bytes": sum(ab.values()), "GBps": sum(ab.values()) / (ms_step * 1e-3) / 1e9,
+                                           "frac": sum(ab.values()) / (ms_step * 1e-3) / 1e9 / peak}}
+        line["gpu_launches"] = int(launches)
+        if e2e_full:
+            line["e2e_full_upload"] = e2e_full
+        if world == 1 and not a.no_cpu_baseline:
+            reps = 2 if P <= 10**6 else 1
+            sc_b, cam_b, dL_b, sample = sc_c, cam_c, dL_c, f"{reps} full step(s) of the workload"
+            if P > 10**6:  # bound the CPU work: same camera, first 1M Gaussians of the cloud
+                sc_b = S.Scene(*[t[:10**6].contiguous() if isinstance(t, torch.Tensor) else t for t in sc_c])
+                sample = "1 step over the first 1M Gaussians of the cloud at full resolution"
+            sec = cpu_port_step_seconds(sc_b, cam_b, settings, dL_b, reps)
+            line["cpu_baseline"] = {"value": pixels / sec / 1e6, "unit": "Mpixels/s", "cores": os.cpu_count(),
+                                    "kind": "port", "sample": sample + " (oracle/stp_oracle.c, OpenMP)",
+                                    "ms_per_step": sec * 1e3}
+    else:
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": e2e_value, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "reference",
+                                "sample": "unmodified reference CUDA build (oracle/_ref, sm_100) on the same GPU, full "
+                                          "workload -- the reference ships no CPU path; host cores only launch kernels"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

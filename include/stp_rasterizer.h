@@ -161,6 +161,14 @@ int stp_requires_cov3D_inv(const StpSettings* settings);
 /* stage timings of the last stp_forward/stp_backward on this thread when debug&2 was set
  * (replaces the viewer-only Timer, rasterizer_impl.h:77-147): ms[0..n) with names[0..n). */
 int stp_last_timings(float* ms, const char** names, int max_n);
+/* Mean stage time over every debug&2 call on this thread since the last summary/reset: mean_ms[0..n),
+ * names[0..n), counts[0..n).  Events are recorded on the caller's stream and resolved here, so the
+ * instrumented calls themselves never synchronise (bench.py uses this for the per-kernel roofline). */
+int stp_timing_summary(float* mean_ms, const char** names, int* counts, int max_n);
+void stp_timing_reset(void);
+/* cumulative number of hand-written kernels this thread has launched through stp_forward/stp_backward
+ * (library kernels such as a CUB sort are NOT counted) -- bench.py reports the per-step difference. */
+long long stp_kernel_launches(void);
 
 const char* stp_last_error(void);
 int stp_abi_version(void);

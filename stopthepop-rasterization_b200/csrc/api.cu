@@ -18,6 +18,7 @@ using namespace stp;
 namespace {
 
 thread_local std::string g_error;
+thread_local long long g_launches = 0;  // hand-written kernels launched by this thread (stp_kernel_launches)
 thread_local std::vector<std::pair<const char*, float>> g_timings;
 
 int fail(int code, const std::string& msg) {
@@ -104,33 +105,51 @@ Frame make_frame(const float* background, int W, int H, const StpTileBand* band,
     return f;
 }
 
+// Stage timer (replaces the viewer-only Timer, rasterizer_impl.h:77-147).  Armed by debug&2.  Events are
+// recorded on the caller's stream and resolved LAZILY (stp_last_timings / stp_timing_summary), so an
+// instrumented call adds a few event records but no host<->device synchronisation to the timed region.
+struct StageSample {
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+};
+thread_local std::vector<StageSample> g_pending;
+constexpr size_t kMaxPending = 8192;
+
 struct StageTimer {
     bool on;
     cudaStream_t stream;
-    std::vector<cudaEvent_t> ev;
-    std::vector<const char*> names;
-    StageTimer(bool on_, cudaStream_t s) : on(on_), stream(s) { mark(nullptr); }
+    StageSample cur;
+    StageTimer(bool on_, cudaStream_t s) : on(on_ && g_pending.size() < kMaxPending), stream(s) { mark(nullptr); }
     void mark(const char* name) {
         if (!on) return;
         cudaEvent_t e;
         cudaEventCreate(&e);
         cudaEventRecord(e, stream);
-        ev.push_back(e);
-        names.push_back(name);
+        cur.ev.push_back(e);
+        cur.names.push_back(name);
     }
     void finish() {
         if (!on) return;
-        cudaEventSynchronize(ev.back());
-        g_timings.clear();
-        for (size_t i = 1; i < ev.size(); ++i) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-            g_timings.push_back({names[i], ms});
-        }
-        for (auto e : ev) cudaEventDestroy(e);
-        ev.clear();
+        g_pending.push_back(std::move(cur));
+        on = false;
     }
 };
+
+void resolve_sample(StageSample& smp, std::vector<std::pair<const char*, float>>& out) {
+    out.clear();
+    if (smp.ev.empty()) return;
+    cudaEventSynchronize(smp.ev.back());
+    for (size_t i = 1; i < smp.ev.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, smp.ev[i - 1], smp.ev[i]);
+        out.push_back({smp.names[i], ms});
+    }
+}
+void destroy_pending() {
+    for (auto& smp : g_pending)
+        for (auto e : smp.ev) cudaEventDestroy(e);
+    g_pending.clear();
+}
 
 }  // namespace
 
@@ -140,6 +159,7 @@ const char* stp_last_error(void) { return g_error.c_str(); }
 int stp_abi_version(void) { return STP_ABI_VERSION; }
 
 int stp_last_timings(float* ms, const char** names, int max_n) {
+    if (!g_pending.empty()) resolve_sample(g_pending.back(), g_timings);
     int n = 0;
     for (auto& t : g_timings) {
         if (n >= max_n) break;
@@ -149,6 +169,38 @@ int stp_last_timings(float* ms, const char** names, int max_n) {
     }
     return n;
 }
+
+int stp_timing_summary(float* mean_ms, const char** names, int* counts, int max_n) {
+    std::vector<std::pair<const char*, float>> one;
+    std::vector<const char*> nm;
+    std::vector<double> sum;
+    std::vector<int> cnt;
+    for (auto& smp : g_pending) {
+        resolve_sample(smp, one);
+        for (auto& t : one) {
+            size_t k = 0;
+            while (k < nm.size() && std::strcmp(nm[k], t.first) != 0) ++k;
+            if (k == nm.size()) {
+                nm.push_back(t.first);
+                sum.push_back(0.0);
+                cnt.push_back(0);
+            }
+            sum[k] += t.second;
+            cnt[k] += 1;
+        }
+    }
+    destroy_pending();
+    int n = 0;
+    for (size_t k = 0; k < nm.size() && n < max_n; ++k, ++n) {
+        mean_ms[n] = (float)(sum[k] / cnt[k]);
+        names[n] = nm[k];
+        counts[n] = cnt[k];
+    }
+    return n;
+}
+
+void stp_timing_reset(void) { destroy_pending(); }
+long long stp_kernel_launches(void) { return g_launches; }
 
 int stp_requires_cov3D_inv(const StpSettings* s) {
     if (s == nullptr) return 0;
@@ -251,6 +303,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     pa.prefiltered = prefiltered != 0;
     pa.radii = radii;
     STP_CUDA(launch_preprocess(pa, f, g, s.tile_based_culling, stream), "preprocess");
+    g_launches += 1;
     timer.mark("Preprocess");
 
     uint32_t R = 0;
@@ -269,11 +322,13 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
 
     if (R > 0) {
         STP_CUDA(launch_duplicate(P, f, s, g, radii, b.keys_unsorted, b.point_list_unsorted, stream), "duplicate");
+        g_launches += 1;
     }
     timer.mark("Duplicate");
     const int bit = (int)higher_msb((uint32_t)tiles);
     STP_CUDA(launch_sort(b, (size_t)R, 32 + bit, stream), "sort");
     STP_CUDA(launch_tile_ranges((size_t)R, b.keys, img.ranges, tiles, stream), "tile ranges");
+    g_launches += (R > 0) + sort_kernel_launches((size_t)R, 32 + bit);
     timer.mark("Sort");
 
     RenderArgs ra;
@@ -291,6 +346,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     } else {
         STP_CUDA(launch_render_hier_fwd(f, s, ra, stream), "render (HIER)");
     }
+    g_launches += 1;
     timer.mark("Render");
     timer.finish();
     return STP_OK;
@@ -349,6 +405,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
             STP_CUDA(launch_render_hier_bwd(f, s, ra, stream), "render backward (HIER)");
         }
     }
+    g_launches += (R > 0);
     timer.mark("RenderBackward");
 
     PreprocessBwdArgs pa;
@@ -361,6 +418,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     pa.dL_dmean3D = dL_dmean3D; pa.dL_dcolor = dL_dcolor; pa.dL_dcov3D = dL_dcov3D; pa.dL_dsh = dL_dsh;
     pa.dL_dscale = dL_dscale; pa.dL_drot = dL_drot;
     STP_CUDA(launch_preprocess_bwd(pa, f, stream), "preprocess backward");
+    g_launches += 1;
     timer.mark("PreprocessBackward");
     timer.finish();
     return STP_OK;

@@ -213,6 +213,7 @@ cudaError_t launch_duplicate(int P, const Frame& f, const Settings& s, const Geo
 }
 
 size_t sort_temp_bytes(size_t R) { return radix_sort_temp_bytes(R); }
+int sort_kernel_launches(size_t R, int end_bit) { return radix_sort_kernel_launches(R, end_bit); }
 
 cudaError_t launch_sort(BinningState& b, size_t R, int end_bit, cudaStream_t stream) {
     return radix_sort_pairs(b.sort_space, b.sort_bytes, b.keys_unsorted, b.keys, b.point_list_unsorted, b.point_list, R,

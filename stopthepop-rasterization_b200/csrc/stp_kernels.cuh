@@ -78,6 +78,7 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* vm, ui
 
 // binning.cu
 size_t sort_temp_bytes(size_t R);
+int sort_kernel_launches(size_t R, int end_bit);  // own kernels per sort (0 while the sort is a library call)
 cudaError_t launch_duplicate(int P, const Frame& f, const Settings& s, const GeometryState& g, const int* radii,
                              uint64_t* keys, uint32_t* values, cudaStream_t stream);
 cudaError_t launch_sort(BinningState& b, size_t R, int end_bit, cudaStream_t stream);

@@ -72,6 +72,10 @@ _lib.stp_view_binning.argtypes = [_P, ctypes.c_int, ctypes.POINTER(StpBinningVie
 _lib.stp_view_image.argtypes = [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(StpImageView)]
 _lib.stp_mark_visible.argtypes = [ctypes.c_int, _P, _P, _P, _P, _P]
 _lib.stp_last_timings.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_char_p), ctypes.c_int]
+_lib.stp_timing_summary.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_char_p),
+                                    ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+_lib.stp_timing_reset.restype = None
+_lib.stp_kernel_launches.restype = ctypes.c_longlong
 _lib.stp_forward.restype = ctypes.c_int
 _lib.stp_forward.argtypes = [
     ALLOC_FN, _P, ALLOC_FN, _P, ALLOC_FN, _P,  # arenas
@@ -188,20 +192,23 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy,
                                  pixel_colors, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                 imageBuffer, settings_dict, debug, tile_band=None):
+                                 imageBuffer, settings_dict, debug, tile_band=None, want_param_slab=False):
     device = means3D.device
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)  # rasterize_points.cu:169-170
     M = sh.size(1) if sh is not None and sh.numel() != 0 else 0
     st = settings_from_dict(settings_dict)
-    # one zero-filled slab instead of nine torch::zeros (rasterize_points.cu:178-186)
-    widths = [3, 3, 3, 4, 1, 6, 3 * M, 3, 4]  # means3D means2D colors conic opacity cov3D sh scales rot
+    # one zero-filled slab instead of nine torch::zeros (rasterize_points.cu:178-186).  The five PARAMETER
+    # gradients come first and contiguous, so a data-parallel caller can all-reduce them as one buffer
+    # (parallel.py); the per-view intermediates (means2D, colors, conic, cov3D) follow.
+    widths = [3, 3 * M, 1, 3, 4, 3, 3, 4, 6]  # means3D sh opacity scales rot | means2D colors conic cov3D
     flat = torch.zeros((sum(widths) * P,), dtype=torch.float32, device=device)
     views, off = [], 0
     for w in widths:
         views.append(flat[off:off + w * P])
         off += w * P
-    dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dconic, dL_dopacity, dL_dcov3D, dL_dsh, dL_dscales, dL_drot = views
+    dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drot, dL_dmeans2D, dL_dcolors, dL_dconic, dL_dcov3D = views
+    param_slab = flat[:sum(widths[:5]) * P]
     if P != 0:
         means3D = _f32(means3D, device)
         keep = [_f32(t, device) for t in (background, opacities, colors, scales, rotations, cov3D_precomp, viewmatrix,
@@ -222,8 +229,9 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
                                    int(debug), _stream(device))
         if rc != 0:
             raise RuntimeError(_err())
-    return (dL_dmeans2D.view(P, 3), dL_dcolors.view(P, NUM_CHANNELS), dL_dopacity.view(P, 1), dL_dmeans3D.view(P, 3),
-            dL_dcov3D.view(P, 6), dL_dsh.view(P, M, 3), dL_dscales.view(P, 3), dL_drot.view(P, 4))
+    grads8 = (dL_dmeans2D.view(P, 3), dL_dcolors.view(P, NUM_CHANNELS), dL_dopacity.view(P, 1), dL_dmeans3D.view(P, 3),
+              dL_dcov3D.view(P, 6), dL_dsh.view(P, M, 3), dL_dscales.view(P, 3), dL_drot.view(P, 4))
+    return (grads8, param_slab) if want_param_slab else grads8
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):
@@ -287,3 +295,21 @@ def last_timings():
     names = (ctypes.c_char_p * 16)()
     n = _lib.stp_last_timings(ms, names, 16)
     return [(names[i].decode(), ms[i]) for i in range(n)]
+
+
+def timing_summary():
+    """{stage: (mean_ms, count)} over all debug&2 calls since the last summary/reset (lazy event resolve)."""
+    ms = (ctypes.c_float * 16)()
+    names = (ctypes.c_char_p * 16)()
+    counts = (ctypes.c_int * 16)()
+    n = _lib.stp_timing_summary(ms, names, counts, 16)
+    return {names[i].decode(): (ms[i], counts[i]) for i in range(n)}
+
+
+def timing_reset():
+    _lib.stp_timing_reset()
+
+
+def kernel_launches():
+    """cumulative count of hand-written kernels launched by this thread (library kernels excluded)."""
+    return int(_lib.stp_kernel_launches())

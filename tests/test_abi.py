@@ -1,0 +1,79 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/stp_rasterizer.h
+declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import PKG, ROOT
+
+LIB = os.path.join(PKG, "lib", "libstp_rasterizer.so")
+HEADER = os.path.join(ROOT, "include", "stp_rasterizer.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|size_t|char\s*\*|void)\s+\*?\s*(stp_[a-z0-9_A-Z]+)\s*\(", src, flags=re.M)
+    return sorted(set(names))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+        g.build()
+    return ctypes.CDLL(LIB)
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_functions()
+    for n in ("stp_forward", "stp_backward", "stp_mark_visible", "stp_geometry_bytes", "stp_binning_bytes",
+              "stp_image_bytes", "stp_view_geometry", "stp_view_binning", "stp_view_image", "stp_requires_cov3D_inv",
+              "stp_last_error", "stp_abi_version", "stp_last_timings"):
+        assert n in names, n
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for n in declared_functions():
+        assert hasattr(lib, n), f"{n} declared in include/stp_rasterizer.h but not exported"
+
+
+def test_abi_version_and_arena_sizes(lib):
+    lib.stp_abi_version.restype = ctypes.c_int
+    src = open(HEADER).read()
+    assert lib.stp_abi_version() == int(re.search(r"#define STP_ABI_VERSION (\d+)", src).group(1))
+    lib.stp_geometry_bytes.restype = ctypes.c_size_t
+    lib.stp_geometry_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.stp_image_bytes.restype = ctypes.c_size_t
+    lib.stp_image_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.stp_binning_bytes.restype = ctypes.c_size_t
+    lib.stp_binning_bytes.argtypes = [ctypes.c_int]
+    P = 1000
+    # 87 B per Gaussian of the reference layout minus the 4 B internal_radii we do not keep,
+    # +48 B with the inverse covariance
+    g0, g1 = lib.stp_geometry_bytes(P, 0), lib.stp_geometry_bytes(P, 1)
+    assert g0 >= 83 * P and g1 - g0 >= 48 * P and g1 - g0 < 48 * P + 512
+    assert lib.stp_image_bytes(1920, 1080) >= 8 * 1920 * 1080 + 8 * 120 * 68
+    assert lib.stp_binning_bytes(10) >= 24 * 10
+    assert lib.stp_binning_bytes(0) > 0
+
+
+def test_settings_validation_without_gpu(lib):
+    """unsupported queue sizes are rejected before anything touches the device
+    (forward.cu:455-480 / backward.cu:751-760 throw std::runtime_error)."""
+    from diff_gaussian_rasterization import _C
+    st = _C.StpSettings(3, 0, 64, 9, 4, 0, 0, 0, 0, 0, 0)  # mid queue 9 is not instantiated
+    n = ctypes.c_int(0)
+    cb = _C.ALLOC_FN(lambda u, b: None)
+    rc = _C._lib.stp_forward(cb, None, cb, None, cb, None, 10, 0, 1, None, 16, 16, ctypes.byref(st), None, None, None,
+                             None, None, None, 1.0, None, None, None, None, None, None, 1.0, 1.0, 0, None, None, 0, None,
+                             ctypes.byref(n))
+    assert rc == -2
+    assert b"mid queue size" in _C._lib.stp_last_error()
+    st = _C.StpSettings(1, 0, 64, 8, 4, 0, 0, 0, 0, 0, 0)  # PPX_FULL backward, backward.cu:733-736
+    rc = _C._lib.stp_backward(10, 0, 1, 0, None, 16, 16, ctypes.byref(st), None, *([None] * 5), 1.0, *([None] * 6), 1.0,
+                              1.0, *([None] * 15), 0, None)
+    assert rc == -2
+    assert b"Backward not supported for full per-pixel sort" in _C._lib.stp_last_error()

@@ -1,0 +1,271 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes binding
+diff_gaussian_rasterization._C), against
+  (1) the golden fixtures = outputs of the unmodified reference build (tests/golden/*.npz),
+  (2) the CPU oracle on the same inputs,
+  (3) the reference build itself on the same device when oracle/_ref travelled with the repo,
+and, at BASELINE.json's full sizes, size-independent properties (sortedness of every tile list,
+ranges partitioning point_list, determinism of the index buffers, band-sharding reproducing the
+single-GPU buffers).
+
+Bar (north_star): point_list / ranges / radii / n_contrib bit-exact; image and gradients within
+1e-5 relative (gradients: max(1e-5, 10 x the reference's own atomic run-to-run noise)).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CASES, GRAD_NAMES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def run_ours(f, backward=True, band=None, settings=None):
+    from diff_gaussian_rasterization import _C
+    dev = _dev()
+    s = f.scene
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    e = torch.empty(0, device=dev)
+    st = settings or f.settings
+    m3, sc, ro, op, sh = t(s["means3D"]), t(s["scales"]), t(s["rotations"]), t(s["opacities"]), t(f.shs())
+    vm, pm, iv, cp, bg = t(s["viewmatrix"]), t(s["projmatrix"]), t(s["inv_viewprojmatrix"]), t(s["campos"]), t(s["bg"])
+    tx, ty = float(s["tanfovx"]), float(s["tanfovy"])
+    out = _C.rasterize_gaussians(bg, m3, e, op, sc, ro, 1.0, e, vm, pm, iv, tx, ty, f.H, f.W, sh, f.deg, cp, False, st,
+                                 False, False, tile_band=band)
+    R, color, radii, geom, binning, img = out
+    res = dict(R=R, out_color=color, radii=radii, geom=_C.view_geometry(geom, f.P, st),
+               binning=_C.view_binning(binning, R), image=_C.view_image(img, f.W, f.H))
+    if backward:
+        dL = t(s["dL_dout"])
+        pix = t(f.fx["out_color"]) if settings is None else color
+        grads = _C.rasterize_gaussians_backward(bg, m3, radii, op, e, sc, ro, 1.0, e, vm, pm, iv, tx, ty, pix, dL, sh,
+                                                f.deg, cp, geom, R, binning, img, st, False, tile_band=band)
+        res["grads"] = dict(zip(GRAD_NAMES, grads))
+    torch.cuda.synchronize()
+    return res
+
+
+def npy(x):
+    return x.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference_fixture(golden, name):
+    f = golden(name)
+    fx = f.fx
+    r = run_ours(f, backward=False)
+    vis = fx["radii"] > 0
+    assert r["R"] == int(fx["R"])
+    assert np.array_equal(npy(r["radii"]), fx["radii"])
+    g = r["geom"]
+    for k in ("depths", "means2D", "rects2D", "conic_opacity"):
+        a, b = npy(g[k])[vis], fx["geom_" + k][vis]
+        assert np.array_equal(a.view(np.int32), b.view(np.int32)), k
+    assert np.array_equal(npy(g["tiles_touched"])[vis], fx["geom_tiles_touched"][vis])
+    assert np.array_equal(npy(g["clamped"])[vis], fx["geom_clamped"][vis])
+    assert np.abs(npy(g["rgb"])[vis] - fx["geom_rgb"][vis]).max() <= 1e-6
+    assert np.array_equal(npy(r["binning"]["point_list"]), fx["point_list"])
+    assert np.array_equal(npy(r["image"]["ranges"]), fx["ranges"])
+    if "n_contrib" in fx:
+        assert np.array_equal(npy(r["image"]["n_contrib"]), fx["n_contrib"])
+    scale = np.abs(fx["out_color"]).max()
+    d = np.abs(npy(r["out_color"]) - fx["out_color"])
+    assert d.max() <= TOL * scale, (d.max(), int((d > TOL * scale).sum()))
+    assert np.abs(npy(r["image"]["final_T"]) - fx["final_T"]).max() <= TOL
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c not in ("hier_long", "full_sort", "full_sort_long", "c1_config")])
+def test_backward_matches_reference_fixture(golden, name):
+    f = golden(name)
+    r = run_ours(f, backward=True)
+    if f.hier_cull:
+        # the reference's gradient is corrupted by a race in this configuration
+        # (profiles/r01_reference_hier_cull_bwd_race.txt); the pinned CPU oracle is the checker
+        o = f.oracle()
+        ref = o.backward(f.scene["dL_dout"], f.fx["out_color"])
+        noise = {k: 0.0 for k in GRAD_NAMES}
+    else:
+        ref = {k: f.fx[k] for k in GRAD_NAMES}
+        noise = {k: float(f.fx[k + "_noise"]) for k in GRAD_NAMES}
+    for k in GRAD_NAMES:
+        a, b = npy(r["grads"][k]).reshape(-1), ref[k].reshape(-1)
+        tol = max(TOL, 10.0 * noise[k])
+        rel = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+        assert rel <= tol, (k, rel, tol)
+
+
+def test_full_sort_backward_raises(golden):
+    f = golden("full_sort")
+    with pytest.raises(RuntimeError, match="Backward not supported for full per-pixel sort"):  # backward.cu:733-736
+        run_ours(f, backward=True)
+
+
+@pytest.mark.parametrize("name", ["global_default", "hier_preset", "kbuffer16", "full_sort"])
+def test_forward_matches_cpu_oracle(golden, name):
+    f = golden(name)
+    o = f.oracle()
+    r = run_ours(f, backward=False)
+    assert r["R"] == o.R
+    assert np.array_equal(npy(r["binning"]["point_list"]), o.point_list)
+    assert np.array_equal(npy(r["image"]["ranges"]), o.ranges)
+    assert np.abs(npy(r["out_color"]) - o.out_color).max() <= TOL
+
+
+def test_empty_and_degenerate_inputs():
+    """P == 0 short-circuits to a zero image (rasterize_points.cu:93); a cloud entirely behind the camera
+    renders the background with R == 0."""
+    from diff_gaussian_rasterization import _C
+    import stp_scenes as S
+    dev = _dev()
+    sc, cam = S.make_scene(64, 64, 48, 5)
+    sc, cam = S.to_device(sc, dev), S.to_device(cam, dev)
+    e = torch.empty(0, device=dev)
+    d = S.default_settings_dict()
+    z = torch.zeros(0, 3, device=dev)
+    R, color, radii, *_ = _C.rasterize_gaussians(cam.bg, z, e, torch.zeros(0, 1, device=dev), z, torch.zeros(0, 4, device=dev),
+                                                 1.0, e, cam.viewmatrix, cam.projmatrix, cam.inv_viewprojmatrix,
+                                                 cam.tanfovx, cam.tanfovy, 48, 64, torch.zeros(0, 16, 3, device=dev), 3,
+                                                 cam.campos, False, d, False, False)
+    assert R == 0 and color.abs().max().item() == 0 and radii.numel() == 0
+    for mode in (0, 1, 2, 3):
+        d = S.default_settings_dict(sort_mode=mode)
+        behind = sc.means3D - 1000.0 * torch.tensor([0.0, 0.0, 1.0], device=dev)
+        R, color, radii, geom, binning, img = _C.rasterize_gaussians(
+            cam.bg, behind.contiguous(), e, sc.opacities, sc.scales, sc.rotations, 1.0, e, cam.viewmatrix,
+            cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx, cam.tanfovy, 48, 64, sc.shs, 3, cam.campos, False, d,
+            False, False)
+        assert R == 0 and int(radii.max()) == 0
+        assert torch.allclose(color, cam.bg.view(3, 1, 1).expand(3, 48, 64))
+
+
+def _check_index_invariants(res, P, W, H):
+    """size-independent properties of the binning output."""
+    pl = res["binning"]["point_list"].long()
+    keys = res["binning"]["point_list_keys"]
+    ranges = res["image"]["ranges"].long()
+    R = res["R"]
+    tiles_touched = res["geom"]["tiles_touched"].long()
+    radii = res["radii"]
+    assert int(tiles_touched[radii > 0].sum()) == R
+    # keys sorted (tile-major, then depth); ranges partition [0,R) in tile order
+    assert bool((keys[1:] >= keys[:-1]).all())
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert int(lens.sum()) == R and bool((lens >= 0).all())
+    nz = lens > 0
+    starts = ranges[nz, 0]
+    assert bool((starts[1:] == ranges[nz, 1][:-1]).all()) and (starts.numel() == 0 or int(starts[0]) == 0)
+    tile_of = (keys >> 32)
+    assert bool((tile_of[ranges[nz, 0]] == torch.nonzero(nz).squeeze(1)).all())
+    # every instance refers to a visible Gaussian
+    assert bool((radii[pl] > 0).all())
+
+
+@pytest.mark.parametrize("cfg,mode", [("C2", 0), ("C2", 3)])
+def test_full_size_properties_and_reference(cfg, mode):
+    """BASELINE.json configs[1] (1M Gaussians, 1080p): invariants + run-to-run determinism of the index
+    buffers and image + (when oracle/_ref is present) bit-exact index buffers / 1e-5 image against the
+    reference build on the same device."""
+    import stp_scenes as S
+    from diff_gaussian_rasterization import _C
+    from oracle import ref_api as ref
+    dev = _dev()
+    sc, cam = S.make_config(cfg)
+    sc, cam = S.to_device(sc, dev), S.to_device(cam, dev)
+    P, W, H = sc.means3D.shape[0], cam.image_width, cam.image_height
+    d = S.default_settings_dict(sort_mode=mode)
+    e = torch.empty(0, device=dev)
+
+    def ours():
+        out = _C.rasterize_gaussians(cam.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e,
+                                     cam.viewmatrix, cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx, cam.tanfovy,
+                                     H, W, sc.shs, sc.sh_degree, cam.campos, False, d, False, False)
+        R, color, radii, geom, binning, img = out
+        return out, dict(R=R, out_color=color, radii=radii, geom=_C.view_geometry(geom, P, d),
+                         binning=_C.view_binning(binning, R), image=_C.view_image(img, W, H))
+    o1, r1 = ours()
+    o2, r2 = ours()
+    _check_index_invariants(r1, P, W, H)
+    assert r1["R"] == r2["R"] and torch.equal(r1["binning"]["point_list"], r2["binning"]["point_list"])
+    assert torch.equal(r1["out_color"], r2["out_color"])  # forward is deterministic
+    dL = S.make_upstream_grad(W, H, 2002).to(dev)
+    g = _C.rasterize_gaussians_backward(cam.bg, sc.means3D, o1[2], sc.opacities, e, sc.scales, sc.rotations, 1.0, e,
+                                        cam.viewmatrix, cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx,
+                                        cam.tanfovy, o1[1], dL, sc.shs, sc.sh_degree, cam.campos, o1[3], o1[0], o1[4],
+                                        o1[5], d, False)
+    # linearity of the backward pass in the upstream gradient: bwd(2 dL) == 2 bwd(dL) (power-of-two scaling is exact
+    # up to the atomic summation order)
+    g2 = _C.rasterize_gaussians_backward(cam.bg, sc.means3D, o1[2], sc.opacities, e, sc.scales, sc.rotations, 1.0, e,
+                                         cam.viewmatrix, cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx,
+                                         cam.tanfovy, o1[1], 2.0 * dL, sc.shs, sc.sh_degree, cam.campos, o1[3], o1[0],
+                                         o1[4], o1[5], d, False)
+    for a, b in zip(g, g2):
+        assert (2.0 * a - b).abs().max().item() <= 1e-5 * b.abs().max().item()
+    # Gaussians that were culled receive exactly zero gradient
+    assert g[3][o1[2] == 0].abs().max().item() == 0.0
+    if not ref.available():
+        pytest.skip("oracle/_ref not shipped: reference-build comparison skipped (invariants checked)")
+    rr = ref.forward(sc, cam, d)
+    assert rr[0] == r1["R"]
+    assert torch.equal(rr[2], r1["radii"])
+    assert torch.equal(ref.decode_binning(rr[4], rr[0])["point_list"], r1["binning"]["point_list"])
+    assert torch.equal(ref.decode_image(rr[5], W, H)["ranges"], r1["image"]["ranges"])
+    scale = rr[1].abs().max().item()
+    assert (rr[1] - r1["out_color"]).abs().max().item() <= TOL * scale
+    rg = ref.backward(sc, cam, d, rr, dL)
+    rg2 = ref.backward(sc, cam, d, rr, dL)
+    for a, b, b2 in zip(g, rg, rg2):
+        m = b.abs().max().item()
+        noise = (b - b2).abs().max().item() / max(m, 1e-30)
+        assert (a - b).abs().max().item() <= max(TOL, 10 * noise) * m
+
+
+def test_tile_band_sharding_reproduces_single_gpu_buffers(golden):
+    """concatenating the per-band point lists / images of a tile-row sharding equals the
+    single-GPU result bit for bit, and the summed band gradients equal the full gradients."""
+    f = golden("global_default")
+    full = run_ours(f, backward=True, settings=f.settings)
+    gy = (f.H + 15) // 16
+    cut = gy // 2
+    parts = [run_ours(f, backward=True, band=(0, cut), settings=f.settings),
+             run_ours(f, backward=True, band=(cut, gy), settings=f.settings)]
+    assert sum(p["R"] for p in parts) == full["R"]
+    pl = torch.cat([p["binning"]["point_list"] for p in parts])
+    assert torch.equal(pl, full["binning"]["point_list"])
+    img = torch.zeros_like(full["out_color"])
+    img[:, :cut * 16] = parts[0]["out_color"][:, :cut * 16]
+    img[:, cut * 16:] = parts[1]["out_color"][:, cut * 16:]
+    assert torch.equal(img, full["out_color"])
+    for k in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity"):
+        s = parts[0]["grads"][k] + parts[1]["grads"][k]
+        m = full["grads"][k].abs().max().item()
+        assert (s - full["grads"][k]).abs().max().item() <= 1e-5 * m
+
+
+def test_autograd_api_end_to_end(golden):
+    """GaussianRasterizer through torch.autograd returns gradients in input order (__init__.py:160-172)."""
+    from diff_gaussian_rasterization import ExtendedSettings, GaussianRasterizationSettings, GaussianRasterizer
+    f = golden("global_default")
+    dev = _dev()
+    s = f.scene
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    rs = GaussianRasterizationSettings(f.H, f.W, float(s["tanfovx"]), float(s["tanfovy"]), t(s["bg"]), 1.0,
+                                       t(s["viewmatrix"]), t(s["projmatrix"]), t(s["inv_viewprojmatrix"]), f.deg,
+                                       t(s["campos"]), False, ExtendedSettings.from_dict(f.settings), False, False)
+    leaves = [t(a).requires_grad_(True) for a in (s["means3D"], s["opacities"], f.shs(), s["scales"], s["rotations"])]
+    m3, op, sh, sc, ro = leaves
+    m2 = torch.zeros_like(m3, requires_grad=True)
+    rast = GaussianRasterizer(rs)
+    color, radii = rast(m3, m2, op, shs=sh, scales=sc, rotations=ro)
+    (color * t(s["dL_dout"])).sum().backward()
+    assert np.array_equal(npy(radii), f.fx["radii"])
+    for name, leaf in (("dL_dmeans3D", m3), ("dL_dmeans2D", m2), ("dL_dopacity", op), ("dL_dsh", sh),
+                       ("dL_dscales", sc), ("dL_drot", ro)):
+        b = f.fx[name].reshape(-1)
+        rel = np.abs(npy(leaf.grad).reshape(-1) - b).max() / np.abs(b).max()
+        assert rel <= max(TOL, 10 * float(f.fx[name + "_noise"])), (name, rel)
+    vis = rast.markVisible(m3.detach())
+    assert vis.dtype == torch.bool and int(vis.sum()) >= int((radii > 0).sum())

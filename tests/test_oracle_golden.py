@@ -1,0 +1,101 @@
+"""CPU oracle (oracle/stp_oracle.c) pinned against the golden fixtures.
+
+The fixtures under tests/golden/ are outputs of the UNMODIFIED reference CUDA build run on a B200
+(tests/golden/make_golden.py); the reference itself ships no tests or vectors.
+Bar: integer / index outputs bit-exact; image within 1e-5 (north_star tolerance); gradients within
+max(1e-5, 10 x the reference's own run-to-run atomic noise floor) relative to max|grad|.
+"""
+import numpy as np
+import pytest
+
+from conftest import CASES, GRAD_NAMES
+
+TOL = 1e-5
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.int32)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_forward_matches_reference(golden, name):
+    f = golden(name)
+    o = f.oracle()
+    fx = f.fx
+    vis = fx["radii"] > 0
+    assert o.R == int(fx["R"])
+    assert np.array_equal(o.radii, fx["radii"])
+    assert np.array_equal(o.tiles_touched[vis], fx["geom_tiles_touched"][vis])
+    assert np.array_equal(o.point_list, fx["point_list"])
+    # sort keys: tile id exact; depth bits exact except for PTD_CENTER, where the reference's compiled
+    # FMA contraction of the tile-centre ray differs from the restatement by a few ulp (<= 64) (order unaffected:
+    # point_list above is bit-exact)
+    assert np.array_equal(o.keys >> 32, fx["point_list_keys"] >> 32)
+    dk = np.abs((o.keys & 0xFFFFFFFF) - (fx["point_list_keys"] & 0xFFFFFFFF)).max() if o.R else 0
+    assert dk <= (64 if f.settings["sort_settings"]["sort_order"] == 2 else 0)
+    assert np.array_equal(o.ranges, fx["ranges"])
+    # floats that feed the integer decisions are restated bit-exactly
+    for k in ("depths", "means2D", "conic_opacity"):
+        assert np.array_equal(bits(getattr(o, k)[vis]), bits(fx["geom_" + k][vis])), k
+    # rect extents go through logf under tight_opacity_bounding (forward.cu:153-156): host libm vs. CUDA
+    # logf differ by <= 2 ulp; the integer tile rectangles derived from them (point_list above) agree.
+    assert np.abs(bits(o.rects2D[vis]).astype(np.int64) - bits(fx["geom_rects2D"][vis])).max() <= 2
+    assert np.array_equal(o.clamped[vis], fx["geom_clamped"][vis])
+    assert np.abs(o.rgb[vis] - fx["geom_rgb"][vis]).max() <= 1e-6
+    if "n_contrib" in fx:
+        assert np.array_equal(o.n_contrib, fx["n_contrib"])
+    scale = np.abs(fx["out_color"]).max()
+    assert np.abs(o.out_color - fx["out_color"]).max() <= TOL * scale
+    assert np.abs(o.final_T - fx["final_T"]).max() <= TOL
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c not in ("hier_long", "full_sort", "full_sort_long", "c1_config")])
+def test_oracle_backward_matches_reference(golden, name):
+    f = golden(name)
+    if f.hier_cull:
+        pytest.skip("reference HIER backward with 4x4 culling is racy (profiles/r01_reference_hier_cull_bwd_race.txt); "
+                    "the oracle is checked against finite differences instead (test_oracle_hier_cull_fd)")
+    o = f.oracle()
+    g = o.backward(f.scene["dL_dout"], f.fx["out_color"])
+    for k in GRAD_NAMES:
+        ref = f.fx[k].reshape(-1)
+        tol = max(TOL, 10.0 * float(f.fx[k + "_noise"]))
+        rel = np.abs(g[k].reshape(-1) - ref).max() / max(np.abs(ref).max(), 1e-30)
+        assert rel <= tol, (k, rel, tol)
+
+
+def test_oracle_full_sort_backward_is_unsupported(golden):
+    """backward.cu:733-736 throws for PPX_FULL; the oracle reports the same."""
+    f = golden("full_sort")
+    o = f.oracle()
+    with pytest.raises(RuntimeError, match="Backward not supported"):
+        o.backward(f.scene["dL_dout"], f.fx["out_color"])
+
+
+def test_oracle_hier_cull_fd(golden):
+    """HIER + hierarchical_4x4_culling backward: the reference's own gradient is corrupted by a
+    shared-memory race (e.g. Gaussian 668: reference 4.62, true 0.284), so the oracle is pinned by
+    central finite differences of its (reference-exact) forward instead:
+    d(sum(out*dL))/d(opacity_i) for Gaussians whose loss is smooth in opacity at this step size."""
+    f = golden("hier_cull_only")
+    o = f.oracle()
+    dL = f.scene["dL_dout"]
+    g = o.backward(dL, f.fx["out_color"])
+    from oracle import cpu_oracle as co
+    s = f.scene
+
+    def loss(op):
+        oo = co.Oracle(f.settings, s["means3D"], s["scales"], s["rotations"], op, f.shs(), f.deg, s["viewmatrix"],
+                       s["projmatrix"], s["inv_viewprojmatrix"], s["campos"], s["bg"], float(s["tanfovx"]),
+                       float(s["tanfovy"]), f.W, f.H)
+        return float((oo.out_color.astype(np.float64) * dL).sum())
+    eps = 1e-3
+    for i in (668, 808, 659, 1316):
+        op_p, op_m = s["opacities"].copy(), s["opacities"].copy()
+        op_p[i, 0] += eps
+        op_m[i, 0] -= eps
+        fd = (loss(op_p) - loss(op_m)) / (2 * eps)
+        an = float(g["dL_dopacity"][i, 0])
+        assert abs(fd - an) <= 1e-2 * abs(an), (i, fd, an)
+    # the documented reference defect: its stored gradient for Gaussian 668 is an order of magnitude off
+    assert abs(float(f.fx["dL_dopacity"][668, 0]) - float(g["dL_dopacity"][668, 0])) > 1.0
