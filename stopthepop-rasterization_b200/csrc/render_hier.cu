@@ -1,10 +1,498 @@
-// render_hier.cu -- HIER sort mode (placeholder until the hierarchical kernels land).
+// render_hier.cu -- HIER sort mode: three-level (4x4 tail / 2x2 mid / per-pixel head) streaming depth
+// re-sort fused with front-to-back alpha blending, forward and backward.
+//
+// Replaces: sortGaussiansRayHierarchicaEvaluation (hierarchical_render.cuh:207-935) with its forward
+// (:939-1035) and backward (:1038-1175) kernels.
+//
+// What is kept from the reference is the QUEUE SEMANTICS (which Gaussian is popped when a finite
+// queue is full decides the image):
+//   * the tile list is consumed 32 entries at a time; per 4x4 block the 32 new entries get a depth on
+//     the block-centre ray (optionally after the 4x4 contribution cull), are sorted and merged into
+//     the tail queue (resident entries first on ties); while the tail holds more than 32 entries its
+//     16 smallest leave in groups of 4;
+//   * every 2x2 quad re-evaluates each group on its own ray, rank-sorts it (ties by position) and merges
+//     it into its mid queue (resident first on ties); when the queue holds more than MID-4 entries the
+//     4 smallest go to the four pixels of the quad;
+//   * every pixel first blends its head minimum if the head is full, then evaluates the entry on its
+//     own ray (depth < 0, power > 0, alpha < 1/255 reject) and inserts it by strict '<';
+//   * drain order tail -> mid -> head.
+// How it is done is new: one warp owns two 4x4 blocks (one per half-warp), all queue manipulation is
+// rank based (every lane computes the final position of "its" entries with branch-free counting /
+// binary search and scatters them once) instead of compare-exchange networks with a barrier per
+// stage; queues are addressed through base offsets so popping never moves data; warps of one tile
+// run independently (no CTA barrier in the streaming loop), so a finished 8x4 region retires early.
+// The per-pixel arithmetic is the rounding-pinned sequence of stp_math.cuh.
 #include "stp_kernels.cuh"
+
 namespace stp {
-cudaError_t launch_render_hier_fwd(const Frame&, const Settings&, const RenderArgs&, cudaStream_t) {
-    return cudaErrorNotSupported;
+
+namespace {
+
+constexpr float kFltMax = 3.402823466e+38f;
+constexpr int kTailStride = 80;  // 64 entries + 16 pad: the two blocks of a warp live in disjoint banks
+
+template <int MID>
+struct HierShared {
+    static constexpr int kMidCap = MID - 4;       // resident entries after a pop
+    static constexpr int kMidStride = MID - 3;    // odd stride: the 8 quads of a warp hit distinct banks
+    float tail_d[16 * kTailStride];
+    int tail_id[16 * kTailStride];
+    float new_d[16 * 48];  // 32 entries per block, stride 48 (16-bank offset between the blocks of a warp)
+    int new_id[16 * 48];
+    float mid_d[64 * kMidStride];
+    int mid_id[64 * kMidStride];
+    int out_id[64 * 4];
+    float tail_ray[16 * 3];
+    float mid_ray[64 * 3];
+};
+
+struct GaussRec {
+    float2 xy;
+    float4 co;
+    float ic[6];
+    float ux, uy, uz;
+};
+
+__device__ __forceinline__ void load_inv(const float4* __restrict__ inv, int id, float* ic, float& ux, float& uy, float& uz) {
+    const float4 a = __ldg(inv + 3 * id), b = __ldg(inv + 3 * id + 1), c = __ldg(inv + 3 * id + 2);
+    ic[0] = a.x; ic[1] = a.y; ic[2] = a.z;
+    ic[3] = b.x; ic[4] = b.y; ic[5] = b.z;
+    ux = c.x; uy = c.y; uz = c.z;
 }
-cudaError_t launch_render_hier_bwd(const Frame&, const Settings&, const RenderBwdArgs&, cudaStream_t) {
-    return cudaErrorNotSupported;
+
+// per-pixel blending state
+template <bool BWD>
+struct PixelState;
+template <>
+struct PixelState<false> {
+    float T, C0, C1, C2;
+};
+template <>
+struct PixelState<true> {
+    float T, C0, C1, C2;
+    float T_final, g0, g1, g2, f0, f1, f2;
+};
+
+template <int HEAD, int MID, bool CULL, bool BWD>
+__global__ void __launch_bounds__(256)
+render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Sh = HierShared<MID>;
+    Sh& sh = *reinterpret_cast<Sh*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = lane >> 4, hl = lane & 15;
+    const uint32_t hmask = half ? 0xffff0000u : 0x0000ffffu;
+    const int b = warp * 2 + half;        // 4x4 block inside the tile
+    const int q = hl >> 2, p = hl & 3;    // quad inside the block, pixel inside the quad
+    const int qg = b * 4 + q;             // quad inside the tile
+    const uint32_t qmask = 0xfu << (lane & ~3);
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
+    const int cx = tile_x * 16 + (b & 3) * 4, cy = tile_y * 16 + (b >> 2) * 4;
+    const int px = cx + (q & 1) * 2 + (p & 1), py = cy + (q >> 1) * 2 + (p >> 1);
+    const bool inside = px < f.W && py < f.H;
+    const uint32_t pix_id = (uint32_t)f.W * py + px;
+    const float pxf = (float)px, pyf = (float)py;
+    const size_t plane = (size_t)f.W * f.H;
+
+    const uint2* __restrict__ ranges = BWD ? ab.ranges : a.ranges;
+    const uint32_t* __restrict__ point_list = BWD ? ab.point_list : a.point_list;
+    const float2* __restrict__ means2D = BWD ? ab.means2D : a.means2D;
+    const float4* __restrict__ conic_opacity = BWD ? ab.conic_opacity : a.conic_opacity;
+    const float4* __restrict__ cov3D_inv = BWD ? ab.cov3D_inv : a.cov3D_inv;
+    const float* __restrict__ colors = BWD ? ab.colors : a.colors;
+
+    const RayCam cam = make_raycam(f.inv_viewproj, f.cam_pos, f.W, f.H);
+    const Vec3 ray = view_ray(cam, pxf, pyf);  // the pixel's own ray (no half-pixel offset, :355)
+    if (hl == 0) {
+        const Vec3 r = view_ray(cam, fadd((float)cx, 1.5f), fadd((float)cy, 1.5f));
+        sh.tail_ray[b * 3 + 0] = r.x; sh.tail_ray[b * 3 + 1] = r.y; sh.tail_ray[b * 3 + 2] = r.z;
+    }
+    if (p == 0) {
+        const Vec3 r = view_ray(cam, fadd((float)cx, 0.5f + 2.0f * (q & 1)), fadd((float)cy, 0.5f + 2.0f * (q >> 1)));
+        sh.mid_ray[qg * 3 + 0] = r.x; sh.mid_ray[qg * 3 + 1] = r.y; sh.mid_ray[qg * 3 + 2] = r.z;
+    }
+    __syncwarp();
+
+    PixelState<BWD> ps;
+    ps.T = 1.0f;
+    ps.C0 = ps.C1 = ps.C2 = 0.f;
+    float bg_dot = 0.f;
+    if constexpr (BWD) {
+        ps.T_final = inside ? ab.final_T[pix_id] : 0.f;
+        ps.g0 = ps.g1 = ps.g2 = ps.f0 = ps.f1 = ps.f2 = 0.f;
+        if (inside) {
+            ps.g0 = ab.dL_dpix[pix_id];
+            ps.g1 = ab.dL_dpix[plane + pix_id];
+            ps.g2 = ab.dL_dpix[2 * plane + pix_id];
+            ps.f0 = ab.pixel_colors[pix_id] - ps.T_final * f.background[0];
+            ps.f1 = ab.pixel_colors[plane + pix_id] - ps.T_final * f.background[1];
+            ps.f2 = ab.pixel_colors[2 * plane + pix_id] - ps.T_final * f.background[2];
+        }
+        bg_dot = f.background[0] * ps.g0 + f.background[1] * ps.g1 + f.background[2] * ps.g2;
+    }
+    const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
+    bool active = inside;
+
+    // head queue: sorted by depth, hd[0] is the next to blend
+    float hd[HEAD], hs[HEAD];
+    int hi[HEAD];
+#pragma unroll
+    for (int k = 0; k < HEAD; ++k) {
+        hd[k] = kFltMax;
+        hs[k] = 0.f;
+        hi[k] = -1;
+    }
+    int hcount = 0;
+
+    // ---- blend the head minimum (blend_one, :386-417) -----------------------------------------------------------------
+    auto blend_one = [&]() {
+        --hcount;
+        if (!active) return;
+        const int id = hi[0];
+        if constexpr (!BWD) {
+            const float alpha = hs[0];
+            const float test_T = fmul(ps.T, fsub(1.0f, alpha));
+            if (test_T < kTThreshold) {
+                active = false;
+                return;
+            }
+            ps.C0 = ffma(fmul(__ldg(colors + 3 * id + 0), alpha), ps.T, ps.C0);
+            ps.C1 = ffma(fmul(__ldg(colors + 3 * id + 1), alpha), ps.T, ps.C1);
+            ps.C2 = ffma(fmul(__ldg(colors + 3 * id + 2), alpha), ps.T, ps.C2);
+            ps.T = test_T;
+        } else {
+            const float G = hs[0];
+            const float4 co = __ldg(conic_opacity + id);
+            const float alpha = fminf(0.99f, fmul(co.w, G));
+            const float test_T = fmul(ps.T, fsub(1.0f, alpha));
+            if (test_T < kTThreshold) {
+                active = false;
+                return;
+            }
+            const float2 xy = __ldg(means2D + id);
+            const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
+            const float dchannel_dcolor = alpha * ps.T;
+            const float c0 = __ldg(colors + 3 * id + 0), c1 = __ldg(colors + 3 * id + 1), c2 = __ldg(colors + 3 * id + 2);
+            ps.C0 += c0 * alpha * ps.T;
+            ps.C1 += c1 * alpha * ps.T;
+            ps.C2 += c2 * alpha * ps.T;
+            const float inv_T = 1.0f / test_T;
+            float dL_dalpha = (c0 - (ps.f0 - ps.C0) * inv_T) * ps.g0 + (c1 - (ps.f1 - ps.C1) * inv_T) * ps.g1 +
+                              (c2 - (ps.f2 - ps.C2) * inv_T) * ps.g2;
+            dL_dalpha *= ps.T;
+            dL_dalpha += (-ps.T_final / (1.f - alpha)) * bg_dot;
+            const float dL_dG = co.w * dL_dalpha;
+            const float gdx = G * dx, gdy = G * dy;
+            const float dG_ddelx = -gdx * co.x - gdy * co.y;
+            const float dG_ddely = -gdy * co.z - gdx * co.y;
+            atomicAdd(ab.dL_dcolor + 3 * id + 0, dchannel_dcolor * ps.g0);
+            atomicAdd(ab.dL_dcolor + 3 * id + 1, dchannel_dcolor * ps.g1);
+            atomicAdd(ab.dL_dcolor + 3 * id + 2, dchannel_dcolor * ps.g2);
+            atomicAdd(ab.dL_dmean2D + 3 * id + 0, dL_dG * dG_ddelx * ddelx_dx);
+            atomicAdd(ab.dL_dmean2D + 3 * id + 1, dL_dG * dG_ddely * ddely_dy);
+            atomicAdd(ab.dL_dconic + 4 * id + 0, -0.5f * gdx * dx * dL_dG);
+            atomicAdd(ab.dL_dconic + 4 * id + 1, -0.5f * gdx * dy * dL_dG);
+            atomicAdd(ab.dL_dconic + 4 * id + 3, -0.5f * gdy * dy * dL_dG);
+            atomicAdd(ab.dL_dopacity + id, G * dL_dalpha);
+            ps.T = test_T;
+        }
+#pragma unroll
+        for (int k = 1; k < HEAD; ++k) {
+            hd[k - 1] = hd[k];
+            hs[k - 1] = hs[k];
+            hi[k - 1] = hi[k];
+        }
+        hd[HEAD - 1] = kFltMax;
+    };
+
+    // ---- one entry arrives at the pixel (front4OneFromMid inner body, :421-536) -----------------------------------------
+    auto head_push = [&](int id) {
+        if (hcount >= HEAD) blend_one();
+        if (id < 0 || !active) return;
+        // the cheap rejections first; both are side-effect free, so their order is irrelevant
+        const float2 xy = __ldg(means2D + id);
+        const float4 co = __ldg(conic_opacity + id);
+        const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
+        const float power = gaussian_power(dx, dy, co.x, co.y, co.z);
+        if (power > 0.0f) return;
+        const float G = expf(power);
+        const float alpha = fminf(0.99f, fmul(co.w, G));
+        if (alpha < kAlphaThreshold) return;
+        float ic[6], ux, uy, uz;
+        load_inv(cov3D_inv, id, ic, ux, uy, uz);
+        const float depth = depth_along_ray(ic, ux, uy, uz, ray);
+        if (depth < 0.0f) return;
+        float ed = depth, es = BWD ? G : alpha;
+        int ei = id;
+#pragma unroll
+        for (int k = 0; k < HEAD; ++k) {
+            if (ed < hd[k]) {
+                const float td = hd[k], ts = hs[k];
+                const int ti = hi[k];
+                hd[k] = ed; hs[k] = es; hi[k] = ei;
+                ed = td; es = ts; ei = ti;
+            }
+        }
+        ++hcount;
+    };
+
+    // ---- mid queue of this quad ---------------------------------------------------------------------------------------
+    float* const md = sh.mid_d + qg * Sh::kMidStride;
+    int* const mi = sh.mid_id + qg * Sh::kMidStride;
+    int* const oi = sh.out_id + qg * 4;
+    int mcount = 0, mbase = 0;  // resident entries live at md[mbase .. mbase+mcount)
+    const float mrx = sh.mid_ray[qg * 3], mry = sh.mid_ray[qg * 3 + 1], mrz = sh.mid_ray[qg * 3 + 2];
+
+    // the 4 smallest mid entries (already in oi[0..3]) go to the 4 pixels of the quad
+    auto quad_to_head = [&]() {
+        const bool any = __any_sync(qmask, active);
+        if (!any) return;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) head_push(oi[k]);
+    };
+
+    // one group of 4 tail entries (ids g_id[0..3], quad lane p owns entry p) enters the mid queue (:566-677)
+    auto mid_push_group = [&](int my_id) {
+        float my_d = kFltMax;
+        if (my_id >= 0) {
+            float ic[6], ux, uy, uz;
+            load_inv(cov3D_inv, my_id, ic, ux, uy, uz);
+            const Vec3 mr{mrx, mry, mrz};
+            my_d = depth_along_ray(ic, ux, uy, uz, mr);
+        }
+        // rank among the 4 new entries, ties by lane (shflRankingLocal, :129-143)
+        float nd[4];
+        int rank = 0;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            nd[o] = __shfl_sync(qmask, my_d, o, 4);
+            rank += (o != p) && (nd[o] < my_d || (nd[o] == my_d && o < p));
+        }
+        // final position of my new entry: rank + #resident <= it (resident first on ties)
+        int pos_new = rank;
+        for (int k = 0; k < mcount; ++k) pos_new += md[mbase + k] <= my_d;
+        // final positions of the resident entries I own (k = p, p+4, ...): k + #new < it
+        float rd[Sh::kMidCap / 4];
+        int ri[Sh::kMidCap / 4], rpos[Sh::kMidCap / 4];
+#pragma unroll
+        for (int j = 0; j < Sh::kMidCap / 4; ++j) {
+            const int k = p + 4 * j;
+            rpos[j] = -1;
+            if (k < mcount) {
+                rd[j] = md[mbase + k];
+                ri[j] = mi[mbase + k];
+                rpos[j] = k + (nd[0] < rd[j]) + (nd[1] < rd[j]) + (nd[2] < rd[j]) + (nd[3] < rd[j]);
+            }
+        }
+        __syncwarp(qmask);
+        const bool pop = mcount + 4 > MID - 4;
+        const int shift = pop ? 4 : 0;
+        if (pos_new >= shift) {
+            md[pos_new - shift] = my_d;
+            mi[pos_new - shift] = my_id;
+        } else {
+            oi[pos_new] = my_id;
+        }
+#pragma unroll
+        for (int j = 0; j < Sh::kMidCap / 4; ++j) {
+            if (rpos[j] >= shift) {
+                md[rpos[j] - shift] = rd[j];
+                mi[rpos[j] - shift] = ri[j];
+            } else if (rpos[j] >= 0) {
+                oi[rpos[j]] = ri[j];
+            }
+        }
+        mbase = 0;
+        mcount = mcount + 4 - shift;
+        __syncwarp(qmask);
+        if (pop) quad_to_head();
+        __syncwarp(qmask);
+    };
+
+    // ---- tail queue of this block -------------------------------------------------------------------------------------
+    float* const td = sh.tail_d + b * kTailStride;
+    int* const ti = sh.tail_id + b * kTailStride;
+    float* const nwd = sh.new_d + b * 48;
+    int* const nwi = sh.new_id + b * 48;
+    int tcount = 0, tbase = 0;  // resident entries live at td[tbase .. tbase+tcount)
+    const Vec3 tray{sh.tail_ray[b * 3], sh.tail_ray[b * 3 + 1], sh.tail_ray[b * 3 + 2]};
+
+    const uint2 range = ranges[tile_y * f.grid_x + tile_x];
+    for (uint32_t progress = range.x; progress < range.y; progress += 32) {
+        if (!__any_sync(0xffffffffu, active)) break;  // per-warp early exit (:692)
+
+        // each lane of the half-warp evaluates 2 of the 32 new entries on the block-centre ray
+        float e_d[2];
+        int e_id[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const uint32_t src = progress + hl + 16 * s;
+            int id = -1;
+            float d = kFltMax;
+            if (src < range.y) id = (int)__ldg(point_list + src);
+            if (id >= 0) {
+                bool culled = false;
+                if constexpr (CULL) {  // :723-743
+                    const float2 xy = __ldg(means2D + id);
+                    const float4 co = __ldg(conic_opacity + id);
+                    float mx, my;
+                    const float pw = max_contrib_power<3, 3>(co.x, co.y, co.z, xy.x, xy.y, (float)cx, (float)cy,
+                                                             fadd((float)cx, 3.0f), fadd((float)cy, 3.0f), mx, my);
+                    culled = fminf(0.99f, fmul(co.w, expf(-pw))) < kAlphaThreshold;
+                }
+                if (!culled) {
+                    float ic[6], ux, uy, uz;
+                    load_inv(cov3D_inv, id, ic, ux, uy, uz);
+                    d = depth_along_ray(ic, ux, uy, uz, tray);
+                } else {
+                    id = -1;
+                }
+            }
+            e_d[s] = d;
+            e_id[s] = (d == kFltMax) ? -1 : id;
+            nwd[hl + 16 * s] = e_d[s];
+            nwi[hl + 16 * s] = e_id[s];
+        }
+        // my resident entries (positions hl, hl+16 of the resident run) before anything is overwritten
+        float r_d[2];
+        int r_id[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int k = hl + 16 * s;
+            r_d[s] = (k < tcount) ? td[tbase + k] : kFltMax;
+            r_id[s] = (k < tcount) ? ti[tbase + k] : -1;
+        }
+        __syncwarp(hmask);
+        const int n_valid = __popc(__ballot_sync(hmask, e_id[0] >= 0)) + __popc(__ballot_sync(hmask, e_id[1] >= 0));
+        // ranks: new entry i -> #new before it (depth, then list position) + #resident <= it;
+        //        resident k -> k + #new < it
+        int rk_new[2] = {0, 0}, sh_res[2] = {0, 0};
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const float dj = nwd[j];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int i = hl + 16 * s;
+                rk_new[s] += (dj < e_d[s]) || (dj == e_d[s] && j < i);
+                sh_res[s] += dj < r_d[s];
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            // binary search: number of resident entries with depth <= e_d[s]
+            int lo = 0, hi_ = tcount;
+            while (lo < hi_) {
+                const int mid = (lo + hi_) >> 1;
+                if (td[tbase + mid] <= e_d[s]) lo = mid + 1; else hi_ = mid;
+            }
+            rk_new[s] += lo;
+        }
+        __syncwarp(hmask);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (e_id[s] >= 0) {
+                td[rk_new[s]] = e_d[s];
+                ti[rk_new[s]] = e_id[s];
+            }
+            const int k = hl + 16 * s;
+            if (k < tcount) {
+                td[k + sh_res[s]] = r_d[s];
+                ti[k + sh_res[s]] = r_id[s];
+            }
+        }
+        tbase = 0;
+        tcount += n_valid;
+        __syncwarp(hmask);
+
+        // pop the 16 smallest while more than 32 are held (at most twice, :827-846)
+#pragma unroll 1
+        for (int rep = 0; rep < 2; ++rep) {
+            if (tcount > 32) {
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) mid_push_group(ti[tbase + 4 * g + p]);
+                tbase += 16;
+                tcount -= 16;
+            }
+        }
+    }
+
+    // ---- drain: tail -> mid -> head (:855-925) ---------------------------------------------------------------------------
+    if (__any_sync(hmask, active)) {
+        while (tcount > 0) {
+            mid_push_group(p < tcount ? ti[tbase + p] : -1);
+            tbase += 4;
+            tcount -= min(tcount, 4);
+        }
+        while (mcount > 0) {
+            __syncwarp(qmask);
+            const int v = mi[mbase + p];
+            __syncwarp(qmask);
+            oi[p] = v;
+            __syncwarp(qmask);
+            mbase += 4;
+            mcount -= 4;
+            quad_to_head();
+        }
+        while (active && hcount > 0) blend_one();
+    }
+
+    if constexpr (!BWD) {
+        if (inside) {
+            a.final_T[pix_id] = ps.T;
+            a.out_color[pix_id] = ffma(ps.T, f.background[0], ps.C0);
+            a.out_color[plane + pix_id] = ffma(ps.T, f.background[1], ps.C1);
+            a.out_color[2 * plane + pix_id] = ffma(ps.T, f.background[2], ps.C2);
+        }
+    }
 }
+
+template <int HEAD, int MID, bool BWD>
+cudaError_t launch_variant(const Frame& f, bool cull, const RenderArgs& a, const RenderBwdArgs& ab, cudaStream_t stream) {
+    dim3 grid(f.grid_x, f.row1 - f.row0, 1);
+    if (grid.y == 0) return cudaSuccess;
+    const size_t smem = sizeof(HierShared<MID>);
+    if (cull) {
+        cudaFuncSetAttribute(render_hier_kernel<HEAD, MID, true, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        render_hier_kernel<HEAD, MID, true, BWD><<<grid, 256, smem, stream>>>(f, a, ab);
+    } else {
+        cudaFuncSetAttribute(render_hier_kernel<HEAD, MID, false, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        render_hier_kernel<HEAD, MID, false, BWD><<<grid, 256, smem, stream>>>(f, a, ab);
+    }
+    return cudaGetLastError();
+}
+
+template <bool BWD>
+cudaError_t dispatch(const Frame& f, const Settings& s, const RenderArgs& a, const RenderBwdArgs& ab, cudaStream_t stream) {
+    // instantiated queue sizes: forward.cu:445-488 (HEAD 4/8/16 x MID 8/12/20), backward.cu:739-767 (+HEAD 12)
+#define STP_HIER_MID(HEAD_)                                                                   \
+    switch (s.q_mid) {                                                                        \
+        case 8: return launch_variant<HEAD_, 8, BWD>(f, s.hier_culling, a, ab, stream);       \
+        case 12: return launch_variant<HEAD_, 12, BWD>(f, s.hier_culling, a, ab, stream);     \
+        case 20: return launch_variant<HEAD_, 20, BWD>(f, s.hier_culling, a, ab, stream);     \
+        default: return cudaErrorInvalidValue;                                                \
+    }
+    switch (s.q_head) {
+        case 4: STP_HIER_MID(4)
+        case 8: STP_HIER_MID(8)
+        case 12:
+            if constexpr (BWD) { STP_HIER_MID(12) } else { return cudaErrorInvalidValue; }
+        case 16: STP_HIER_MID(16)
+        default: return cudaErrorInvalidValue;
+    }
+#undef STP_HIER_MID
+}
+
+}  // namespace
+
+cudaError_t launch_render_hier_fwd(const Frame& f, const Settings& s, const RenderArgs& a, cudaStream_t stream) {
+    RenderBwdArgs dummy{};
+    return dispatch<false>(f, s, a, dummy, stream);
+}
+
+cudaError_t launch_render_hier_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream) {
+    RenderArgs dummy{};
+    return dispatch<true>(f, s, dummy, a, stream);
+}
+
 }  // namespace stp
