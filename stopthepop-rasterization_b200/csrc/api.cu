@@ -275,8 +275,6 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
         return fail(STP_ERR_INVALID_ARGUMENT, "provide scales+rotations or cov3D_precomp");
     if (s.requires_inv() && (scales == nullptr || rotations == nullptr))
         return fail(STP_ERR_INVALID_ARGUMENT, "depth-along-ray sort modes need scales and rotations (forward.cu:208-211)");
-    if (s.sort_mode == STP_SORT_PPX_FULL || s.sort_mode == STP_SORT_PPX_KBUFFER)
-        return fail(STP_ERR_UNSUPPORTED, "sort mode not built yet in this round (PPX_FULL / PPX_KBUFFER)");
 
     Frame f = make_frame(background, width, height, band, viewmatrix, projmatrix, inv_viewprojmatrix, cam_pos, tan_fovx,
                          tan_fovy);
@@ -343,6 +341,10 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     ra.out_color = out_color;
     if (s.sort_mode == STP_SORT_GLOBAL) {
         STP_CUDA(launch_render_global_fwd(f, ra, stream), "render (GLOBAL)");
+    } else if (s.sort_mode == STP_SORT_PPX_KBUFFER) {
+        STP_CUDA(launch_render_kbuffer_fwd(f, s, ra, stream), "render (PPX_KBUFFER)");
+    } else if (s.sort_mode == STP_SORT_PPX_FULL) {
+        STP_CUDA(launch_render_full_fwd(f, ra, stream), "render (PPX_FULL)");
     } else {
         STP_CUDA(launch_render_hier_fwd(f, s, ra, stream), "render (HIER)");
     }
@@ -368,7 +370,6 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     if (P <= 0) return STP_OK;  // rasterize_points.cu:191
     if (s.sort_mode == STP_SORT_PPX_FULL)
         return fail(STP_ERR_UNSUPPORTED, "Backward not supported for full per-pixel sort");  // backward.cu:735
-    if (s.sort_mode == STP_SORT_PPX_KBUFFER) return fail(STP_ERR_UNSUPPORTED, "PPX_KBUFFER not built yet in this round");
     if (!geom_buffer || !binning_buffer || !image_buffer) return fail(STP_ERR_INVALID_ARGUMENT, "null arena");
 
     Frame f = make_frame(background, width, height, band, viewmatrix, projmatrix, inv_viewprojmatrix, cam_pos, tan_fovx,
@@ -401,6 +402,8 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     if (R > 0) {
         if (s.sort_mode == STP_SORT_GLOBAL) {
             STP_CUDA(launch_render_global_bwd(f, ra, stream), "render backward (GLOBAL)");
+        } else if (s.sort_mode == STP_SORT_PPX_KBUFFER) {
+            STP_CUDA(launch_render_kbuffer_bwd(f, s, ra, stream), "render backward (PPX_KBUFFER)");
         } else {
             STP_CUDA(launch_render_hier_bwd(f, s, ra, stream), "render backward (HIER)");
         }

@@ -1,0 +1,430 @@
+// render_ppx.cu -- per-pixel re-sorting modes: PPX_KBUFFER (forward + backward) and PPX_FULL (forward).
+//
+// Replaces: renderkBufferCUDA<3,W> (resorted_render.cuh:17-221), renderkBufferBackwardCUDA<3,W>
+// (:223-471) and renderSortedFullCUDA<3> (:474-675).
+//
+// K-buffer: one thread per pixel keeps a depth-sorted window of W candidates in registers; a candidate
+// enters only after passing the alpha test and the depth-along-ray >= 0 test, and the window minimum is
+// blended whenever the window is full.  The tile list is staged through shared memory 256 entries at a
+// time (xy + conic/opacity + id); the 48-byte inverse covariance is fetched only for candidates that
+// survive the alpha test.
+//
+// Full sort: the reference sorts, for EVERY pixel, a sliding window of 4x256 list entries by the pixel's
+// ray depth with a CTA-wide radix sort and lets one thread blend (256 pixels serially per CTA).  Here one
+// WARP owns a pixel at a time: the 1024-entry window lives in registers (32 keys + 32 ids per lane) and is
+// ordered with a register/shuffle bitonic network; the 8 warps of a CTA work on 8 pixels concurrently.
+// Window semantics are the reference's (:560-672): round r adds list entries [256(r+3), 256(r+4)) (round 0
+// starts from the first 1024), sorts, emits the 256 smallest in order, keeps the rest.  The sort is exact
+// for lists <= 1024 entries, like the reference.
+#include "stp_kernels.cuh"
+
+namespace stp {
+
+namespace {
+
+constexpr float kFltMax = 3.402823466e+38f;
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ void load_inv(const float4* __restrict__ inv, int id, float* ic, float& ux, float& uy, float& uz) {
+    const float4 a = __ldg(inv + 3 * id), b = __ldg(inv + 3 * id + 1), c = __ldg(inv + 3 * id + 2);
+    ic[0] = a.x; ic[1] = a.y; ic[2] = a.z;
+    ic[3] = b.x; ic[4] = b.y; ic[5] = b.z;
+    ux = c.x; uy = c.y; uz = c.z;
+}
+
+// ================================================= k-buffer ==========================================================
+template <int WIN, bool BWD>
+__global__ void __launch_bounds__(kBlock)
+render_kbuffer_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
+    __shared__ int s_id[kBlock];
+    __shared__ float2 s_xy[kBlock];
+    __shared__ float4 s_co[kBlock];
+
+    const int tid = threadIdx.x;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
+    const uint32_t px = tile_x * 16 + (tid & 15), py = tile_y * 16 + (tid >> 4);
+    const bool inside = px < (uint32_t)f.W && py < (uint32_t)f.H;
+    const uint32_t pix_id = (uint32_t)f.W * py + px;
+    const float pxf = (float)px, pyf = (float)py;
+    const size_t plane = (size_t)f.W * f.H;
+
+    const uint2* __restrict__ ranges = BWD ? ab.ranges : a.ranges;
+    const uint32_t* __restrict__ point_list = BWD ? ab.point_list : a.point_list;
+    const float2* __restrict__ means2D = BWD ? ab.means2D : a.means2D;
+    const float4* __restrict__ conic_opacity = BWD ? ab.conic_opacity : a.conic_opacity;
+    const float4* __restrict__ cov3D_inv = BWD ? ab.cov3D_inv : a.cov3D_inv;
+    const float* __restrict__ colors = BWD ? ab.colors : a.colors;
+
+    const RayCam cam = make_raycam(f.inv_viewproj, f.cam_pos, f.W, f.H);
+    const Vec3 ray = view_ray(cam, pxf, pyf);
+
+    const uint2 range = ranges[tile_y * f.grid_x + tile_x];
+    int todo = (int)(range.y - range.x);
+    const int rounds = (todo + kBlock - 1) / kBlock;
+
+    bool done = !inside;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint32_t contributor = 0;
+    float T_final = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f, bg_dot = 0.f;
+    if constexpr (BWD) {
+        if (inside) {
+            T_final = ab.final_T[pix_id];
+            g0 = ab.dL_dpix[pix_id];
+            g1 = ab.dL_dpix[plane + pix_id];
+            g2 = ab.dL_dpix[2 * plane + pix_id];
+            f0 = ab.pixel_colors[pix_id] - T_final * f.background[0];
+            f1 = ab.pixel_colors[plane + pix_id] - T_final * f.background[1];
+            f2 = ab.pixel_colors[2 * plane + pix_id] - T_final * f.background[2];
+        }
+        bg_dot = f.background[0] * g0 + f.background[1] * g1 + f.background[2] * g2;
+    }
+    const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
+
+    float wd[WIN], ws[WIN];
+    int wi[WIN];
+#pragma unroll
+    for (int k = 0; k < WIN; ++k) {
+        wd[k] = kFltMax;
+        ws[k] = 0.f;
+        wi[k] = -1;
+    }
+    int wnum = 0;
+
+    auto blend_one = [&]() {
+        if (wnum == 0) return;
+        --wnum;
+        const int id = wi[0];
+        if constexpr (!BWD) {
+            const float alpha = ws[0];
+            const float test_T = fmul(T, fsub(1.0f, alpha));
+            if (test_T < kTThreshold) {
+                done = true;
+                return;
+            }
+            C0 = ffma(fmul(__ldg(colors + 3 * id + 0), alpha), T, C0);
+            C1 = ffma(fmul(__ldg(colors + 3 * id + 1), alpha), T, C1);
+            C2 = ffma(fmul(__ldg(colors + 3 * id + 2), alpha), T, C2);
+            T = test_T;
+        } else {
+            const float G = ws[0];
+            const float4 co = __ldg(conic_opacity + id);
+            const float alpha = fminf(0.99f, fmul(co.w, G));
+            const float test_T = fmul(T, fsub(1.0f, alpha));
+            if (test_T < kTThreshold) {
+                done = true;
+                return;
+            }
+            const float2 xy = __ldg(means2D + id);
+            const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
+            const float dchannel_dcolor = alpha * T;
+            const float c0 = __ldg(colors + 3 * id + 0), c1 = __ldg(colors + 3 * id + 1), c2 = __ldg(colors + 3 * id + 2);
+            C0 += c0 * alpha * T;
+            C1 += c1 * alpha * T;
+            C2 += c2 * alpha * T;
+            const float inv_T = 1.0f / test_T;
+            float dL_dalpha = (c0 - (f0 - C0) * inv_T) * g0 + (c1 - (f1 - C1) * inv_T) * g1 + (c2 - (f2 - C2) * inv_T) * g2;
+            dL_dalpha *= T;
+            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+            const float dL_dG = co.w * dL_dalpha;
+            const float gdx = G * dx, gdy = G * dy;
+            const float dG_ddelx = -gdx * co.x - gdy * co.y;
+            const float dG_ddely = -gdy * co.z - gdx * co.y;
+            atomicAdd(ab.dL_dcolor + 3 * id + 0, dchannel_dcolor * g0);
+            atomicAdd(ab.dL_dcolor + 3 * id + 1, dchannel_dcolor * g1);
+            atomicAdd(ab.dL_dcolor + 3 * id + 2, dchannel_dcolor * g2);
+            atomicAdd(ab.dL_dmean2D + 3 * id + 0, dL_dG * dG_ddelx * ddelx_dx);
+            atomicAdd(ab.dL_dmean2D + 3 * id + 1, dL_dG * dG_ddely * ddely_dy);
+            atomicAdd(ab.dL_dconic + 4 * id + 0, -0.5f * gdx * dx * dL_dG);
+            atomicAdd(ab.dL_dconic + 4 * id + 1, -0.5f * gdx * dy * dL_dG);
+            atomicAdd(ab.dL_dconic + 4 * id + 3, -0.5f * gdy * dy * dL_dG);
+            atomicAdd(ab.dL_dopacity + id, G * dL_dalpha);
+            T = test_T;
+        }
+#pragma unroll
+        for (int k = 1; k < WIN; ++k) {
+            wd[k - 1] = wd[k];
+            ws[k - 1] = ws[k];
+            wi[k - 1] = wi[k];
+        }
+        wd[WIN - 1] = kFltMax;
+    };
+
+    for (int r = 0; r < rounds; ++r, todo -= kBlock) {
+        if (__syncthreads_and(done)) break;
+        const uint32_t src = range.x + r * kBlock + tid;
+        if (src < range.y) {
+            const int id = (int)__ldg(point_list + src);
+            s_id[tid] = id;
+            if (id >= 0) {
+                s_xy[tid] = __ldg(means2D + id);
+                s_co[tid] = __ldg(conic_opacity + id);
+            }
+        }
+        __syncthreads();
+        const int n = min(kBlock, todo);
+        for (int j = 0; !done && j < n; ++j) {
+            if (wnum == WIN) blend_one();
+            if (done) break;
+            ++contributor;
+            const int id = s_id[j];
+            if (id < 0) break;  // padding entries only exist behind the last valid tile
+            const float2 xy = s_xy[j];
+            const float4 co = s_co[j];
+            const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
+            float G;
+            if constexpr (!BWD) {  // forward spelling: positive factor, exp(-x)  (:165-173)
+                const float pw = opacity_factor(dx, dy, co.x, co.y, co.z);
+                if (pw < 0.0f) continue;
+                G = expf(-pw);
+            } else {  // backward spelling (:431-435)
+                const float pw = gaussian_power(dx, dy, co.x, co.y, co.z);
+                if (pw > 0.0f) continue;
+                G = expf(pw);
+            }
+            const float alpha = fminf(0.99f, fmul(co.w, G));
+            if (alpha < kAlphaThreshold) continue;
+            float ic[6], ux, uy, uz;
+            load_inv(cov3D_inv, id, ic, ux, uy, uz);
+            const float depth = depth_along_ray(ic, ux, uy, uz, ray);
+            if (depth < 0.0f) continue;
+            float ed = depth, es = BWD ? G : alpha;
+            int ei = id;
+#pragma unroll
+            for (int k = 0; k < WIN; ++k) {
+                if (ed < wd[k]) {
+                    const float td = wd[k], ts = ws[k];
+                    const int ti = wi[k];
+                    wd[k] = ed; ws[k] = es; wi[k] = ei;
+                    ed = td; es = ts; ei = ti;
+                }
+            }
+            ++wnum;
+        }
+    }
+    if (!done) {
+        while (wnum > 0 && !done) blend_one();
+    }
+    if constexpr (!BWD) {
+        if (inside) {
+            a.final_T[pix_id] = T;
+            a.n_contrib[pix_id] = contributor;
+            a.out_color[pix_id] = ffma(T, f.background[0], C0);
+            a.out_color[plane + pix_id] = ffma(T, f.background[1], C1);
+            a.out_color[2 * plane + pix_id] = ffma(T, f.background[2], C2);
+        }
+    }
+}
+
+// ================================================= full sort =========================================================
+// window element e (0..1023) lives in lane (e & 31), register (e >> 5): a compare-exchange with partner
+// distance < 32 is a shuffle, distance >= 32 is register-local.
+// Window payload v = (list index << 10) | ord, ord = the element's position in the reference's BLOCKED
+// arrangement (thread*4 + item, resorted_render.cuh:560-600) -- cub::BlockRadixSort is stable in that
+// order, so (key, ord) is the reference's total order and equal ray depths (they do occur) resolve
+// identically.  Padding entries are (FLT_MAX, -1).  List index < 2^21 per tile.
+__device__ __forceinline__ bool kv_less(float ka, int va, float kb, int vb) {
+    return ka < kb || (ka == kb && (va & 1023) < (vb & 1023));
+}
+
+// full bitonic sort of 1024 (key, payload) pairs held as k[32], v[32] per lane, ascending by (key, ord).
+__device__ __forceinline__ void bitonic_sort_1024(float (&k)[32], int (&v)[32], int lane) {
+#pragma unroll 1
+    for (int size = 2; size <= 1024; size <<= 1) {
+#pragma unroll 1
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                switch (stride >> 5) {
+#define STP_REG_STAGE(RS)                                                                       \
+    case RS: {                                                                                  \
+        _Pragma("unroll") for (int r = 0; r < 32; ++r) {                                        \
+            if ((r & RS) == 0) {                                                                \
+                const bool up = (((r << 5) | lane) & size) == 0;                                \
+                const bool sw = up ? kv_less(k[r | RS], v[r | RS], k[r], v[r])                  \
+                                   : kv_less(k[r], v[r], k[r | RS], v[r | RS]);                 \
+                const float tk = sw ? k[r | RS] : k[r];                                         \
+                const float uk = sw ? k[r] : k[r | RS];                                         \
+                const int tv = sw ? v[r | RS] : v[r];                                           \
+                const int uv = sw ? v[r] : v[r | RS];                                           \
+                k[r] = tk; k[r | RS] = uk; v[r] = tv; v[r | RS] = uv;                           \
+            }                                                                                   \
+        }                                                                                       \
+    } break;
+                    STP_REG_STAGE(1)
+                    STP_REG_STAGE(2)
+                    STP_REG_STAGE(4)
+                    STP_REG_STAGE(8)
+                    STP_REG_STAGE(16)
+#undef STP_REG_STAGE
+                    default: break;
+                }
+            } else {
+                const bool lower = (lane & stride) == 0;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const bool up = (((r << 5) | lane) & size) == 0;
+                    const float ok = __shfl_xor_sync(0xffffffffu, k[r], stride);
+                    const int ov = __shfl_xor_sync(0xffffffffu, v[r], stride);
+                    // the lower lane keeps the smaller element when sorting upwards
+                    const bool take = (lower == up) ? kv_less(ok, ov, k[r], v[r]) : kv_less(k[r], v[r], ok, ov);
+                    k[r] = take ? ok : k[r];
+                    v[r] = take ? ov : v[r];
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+render_full_kernel(Frame f, RenderArgs a) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
+    const size_t plane = (size_t)f.W * f.H;
+    const RayCam cam = make_raycam(f.inv_viewproj, f.cam_pos, f.W, f.H);
+    const uint2 range = a.ranges[tile_y * f.grid_x + tile_x];
+    const int n = (int)(range.y - range.x);
+    const int rounds = (n + 255) / 256;
+
+    // warp w renders the 32 pixels of rows 2w, 2w+1 of the tile, one after the other
+    for (int pi = 0; pi < 32; ++pi) {
+        const uint32_t px = tile_x * 16 + (pi & 15), py = tile_y * 16 + warp * 2 + (pi >> 4);
+        if (!(px < (uint32_t)f.W && py < (uint32_t)f.H)) continue;  // warp-uniform
+        const uint32_t pix_id = (uint32_t)f.W * py + px;
+        const float pxf = (float)px, pyf = (float)py;
+        const Vec3 ray = view_ray(cam, pxf, pyf);
+
+        float k[32];
+        int v[32];
+        // the first 768 list entries; slot r*32+lane <- list entry r*32+lane (any placement is equivalent
+        // up to exact key ties), the last 256 slots are refilled every round
+        auto load_slot = [&](int r, int idx, int ord) {
+            float key = kFltMax;
+            int payload = -1;
+            if (idx < n) {
+                const int id = (int)__ldg(a.point_list + range.x + idx);
+                float ic[6], ux, uy, uz;
+                load_inv(a.cov3D_inv, id, ic, ux, uy, uz);
+                key = depth_along_ray(ic, ux, uy, uz, ray);
+                payload = (idx << 10) | ord;
+            }
+            k[r] = key;
+            v[r] = payload;
+        };
+        // list entry idx = i*256 + t (i < 3) sits at blocked position 4t + i + 1 in the reference (:560-575)
+#pragma unroll
+        for (int r = 0; r < 24; ++r) {
+            const int idx = r * 32 + lane;
+            load_slot(r, idx, 4 * (idx & 255) + (idx >> 8) + 1);
+        }
+
+        float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+        uint32_t last_contributor = 0;
+        bool done = false;
+        int todo = n;
+        for (int rd = 0; rd < rounds && !done; ++rd, todo -= 256) {
+#pragma unroll
+            for (int r = 24; r < 32; ++r) {  // the round's 256 new entries take item 0 of every thread (:588-600)
+                const int j = (r - 24) * 32 + lane;
+                load_slot(r, (rd + 3) * 256 + j, 4 * j);
+            }
+            bitonic_sort_1024(k, v, lane);
+            // the 256 smallest are elements 0..255 = registers 0..7.  Every lane evaluates alpha of ITS element;
+            // the accepted ones are then blended in order (sequential transmittance, like the reference's thread 0)
+            const int lim = min(256, todo);
+            bool stop = false;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                if (!stop && !done) {
+                    const int e = r * 32 + lane;
+                    float alpha = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+                    bool accept = false;
+                    if (e < lim && v[r] >= 0) {
+                        const int id = (int)__ldg(a.point_list + range.x + (v[r] >> 10));
+                        const float2 xy = __ldg(a.means2D + id);
+                        const float4 co = __ldg(a.conic_opacity + id);
+                        const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
+                        const float pw = opacity_factor(dx, dy, co.x, co.y, co.z);
+                        if (!(pw < 0.0f)) {
+                            alpha = fminf(0.99f, fmul(co.w, expf(-pw)));
+                            accept = !(alpha < kAlphaThreshold);
+                        }
+                        if (accept) {
+                            c0 = __ldg(a.colors + 3 * id + 0);
+                            c1 = __ldg(a.colors + 3 * id + 1);
+                            c2 = __ldg(a.colors + 3 * id + 2);
+                        }
+                    }
+                    uint32_t m = __ballot_sync(0xffffffffu, accept);
+                    while (m) {
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float al = __shfl_sync(0xffffffffu, alpha, l);
+                        const float b0 = __shfl_sync(0xffffffffu, c0, l), b1 = __shfl_sync(0xffffffffu, c1, l),
+                                    b2 = __shfl_sync(0xffffffffu, c2, l);
+                        const float test_T = fmul(T, fsub(1.0f, al));
+                        if (test_T < kTThreshold) {
+                            done = true;
+                            break;
+                        }
+                        C0 = ffma(fmul(b0, al), T, C0);
+                        C1 = ffma(fmul(b1, al), T, C1);
+                        C2 = ffma(fmul(b2, al), T, C2);
+                        T = test_T;
+                        last_contributor = (uint32_t)(rd * 256 + r * 32 + l + 1);
+                    }
+                    if ((r + 1) * 32 >= lim) stop = true;
+                }
+            }
+            // keep elements 256..1023 as slots 0..767 of the next round
+#pragma unroll
+            for (int r = 0; r < 24; ++r) {  // rank rk = 256 + e' goes to thread rk % 256, item rk / 256 (striped, :664-672)
+                const int e2 = r * 32 + lane;
+                k[r] = k[r + 8];
+                v[r] = v[r + 8] < 0 ? -1 : ((v[r + 8] & ~1023) | (4 * (e2 & 255) + (e2 >> 8) + 1));
+            }
+        }
+        if (lane == 0) {
+            a.final_T[pix_id] = T;
+            a.n_contrib[pix_id] = last_contributor;
+            a.out_color[pix_id] = ffma(T, f.background[0], C0);
+            a.out_color[plane + pix_id] = ffma(T, f.background[1], C1);
+            a.out_color[2 * plane + pix_id] = ffma(T, f.background[2], C2);
+        }
+    }
+}
+
+template <bool BWD>
+cudaError_t dispatch_kbuffer(const Frame& f, int window, const RenderArgs& a, const RenderBwdArgs& ab, cudaStream_t stream) {
+    dim3 grid(f.grid_x, f.row1 - f.row0, 1);
+    if (grid.y == 0) return cudaSuccess;
+#define STP_KB(W_) render_kbuffer_kernel<W_, BWD><<<grid, kBlock, 0, stream>>>(f, a, ab)
+    // window rounding of forward.cu:410-425 / backward.cu:714-731
+    if (window <= 1) STP_KB(1);
+    else if (window <= 2) STP_KB(2);
+    else if (window <= 4) STP_KB(4);
+    else if (window <= 8) STP_KB(8);
+    else if (window <= 12) STP_KB(12);
+    else if (window <= 16) STP_KB(16);
+    else if (window <= 20) STP_KB(20);
+    else STP_KB(24);
+#undef STP_KB
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_render_kbuffer_fwd(const Frame& f, const Settings& s, const RenderArgs& a, cudaStream_t stream) {
+    RenderBwdArgs dummy{};
+    return dispatch_kbuffer<false>(f, s.q_head, a, dummy, stream);
+}
+cudaError_t launch_render_kbuffer_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream) {
+    RenderArgs dummy{};
+    return dispatch_kbuffer<true>(f, s.q_head, dummy, a, stream);
+}
+cudaError_t launch_render_full_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream) {
+    dim3 grid(f.grid_x, f.row1 - f.row0, 1);
+    if (grid.y == 0) return cudaSuccess;
+    render_full_kernel<<<grid, kBlock, 0, stream>>>(f, a);
+    return cudaGetLastError();
+}
+
+}  // namespace stp

@@ -92,6 +92,11 @@ cudaError_t launch_render_global_bwd(const Frame& f, const RenderBwdArgs& a, cud
 cudaError_t launch_render_hier_fwd(const Frame& f, const Settings& s, const RenderArgs& a, cudaStream_t stream);
 cudaError_t launch_render_hier_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream);
 
+// render_ppx.cu
+cudaError_t launch_render_kbuffer_fwd(const Frame& f, const Settings& s, const RenderArgs& a, cudaStream_t stream);
+cudaError_t launch_render_kbuffer_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream);
+cudaError_t launch_render_full_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream);
+
 // preprocess_bwd.cu
 cudaError_t launch_preprocess_bwd(const PreprocessBwdArgs& a, const Frame& f, cudaStream_t stream);
 
