@@ -4,16 +4,25 @@
 // Replaces: renderCUDA<3,false> forward (forward.cu:234-366) and renderCUDA<3> backward
 // (backward.cu:437-595).
 //
-// One CTA per 16x16 tile, one thread per pixel (pixel = tile origin + (tid%16, tid/16), the mapping
-// whose per-pixel arithmetic we must reproduce).  The tile's list is streamed through shared memory
-// in slabs of 256 entries {xy, conic+opacity, rgb}.  All per-(pixel,Gaussian) arithmetic is the
-// rounding-pinned sequence of stp_math.cuh, so the accept/reject decisions (power>0, alpha<1/255,
-// T<1e-4) and therefore final_T / n_contrib are identical to the reference build.
+// One CTA per 16x16 tile, one thread per pixel; warp w owns the 8x4-pixel strip (w&1, w>>1) of the tile.
+// The tile's list is streamed through shared memory in slabs of 256 entries {xy, conic+opacity, rgb}.
 //
-// Backward: every lane of a warp visits the same Gaussian in the same iteration, so the nine
-// per-Gaussian gradient terms are first reduced across the warp with shuffles and only then
-// accumulated per CTA in shared memory; one global float atomic per (tile, Gaussian, term) remains
-// instead of one per (pixel, Gaussian, term) in the reference (backward.cu:561,583-592).
+// Both render kernels are FP32-issue bound, not HBM bound (ncu, profiles/r01a_*: issue slots 90 % busy,
+// DRAM 1 %): the reference evaluates every (pixel, list entry) pair, 256 evaluations per entry and tile,
+// although a typical splat only reaches a few dozen pixels of the tile.  Here the thread that stages
+// entry j of a slab also computes, once, WHICH of the 8 strips the entry can reach: the axis-aligned
+// bounding box of the ellipse { q(d) <= ln(255*opacity) } (inflated, so the test is conservative with
+// respect to the float arithmetic of the per-pixel evaluation) against the strip rectangles -> an
+// 8-bit mask per entry.  A warp then only visits the entries whose mask names its strip (ballot over
+// 32 masks + find-first-set walk, order preserved).  A skipped evaluation could only have ended in the
+// "alpha < 1/255 -> continue" branch, which has no side effect besides the list-position counter (kept
+// arithmetically), so final_T, n_contrib and the image are bit-identical to evaluating everything.
+// All per-(pixel,Gaussian) arithmetic is the rounding-pinned sequence of stp_math.cuh.
+//
+// Backward: the nine per-Gaussian gradient terms are reduced across the warp with a recursive-halving
+// exchange (16 shuffles instead of 45) and accumulated per CTA in shared memory; one global float
+// atomic per (tile, Gaussian, term) remains instead of one per (pixel, Gaussian, term) in the reference
+// (backward.cu:561,583-592).
 #include "stp_kernels.cuh"
 
 namespace stp {
@@ -23,18 +32,43 @@ namespace {
 constexpr int kTile = 16;
 constexpr int kBlock = kTile * kTile;
 
+// Which of the 8 strips (bit = strip index = warp index; strip (sx,sy) = pixels [8sx,8sx+7] x [4sy,4sy+3]
+// of the tile) can contain a pixel with alpha >= 1/255 for this Gaussian?  Conservative: real q(d) <= thr
+// implies |dx| <= sqrt(2 thr C/det), |dy| <= sqrt(2 thr A/det); thr is inflated by 0.1 % + 0.01 and the
+// half-widths by 0.01 px, orders of magnitude more than the rounding error of the evaluated power.
+__device__ __forceinline__ uint32_t strip_mask(float2 xy, float4 co, float tile_x0, float tile_y0) {
+    const float det = co.x * co.z - co.y * co.y;
+    if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f) || !(co.w > 0.0f)) return 0xffu;
+    const float thr = __logf(255.0f * co.w) * 1.001f + 0.01f;
+    if (!(thr > 0.0f)) return 0xffu;
+    const float s = 2.0f * thr / det;
+    const float hx = sqrtf(s * co.z) * 1.0001f + 0.01f, hy = sqrtf(s * co.x) * 1.0001f + 0.01f;
+    if (!(hx < 1e9f) || !(hy < 1e9f)) return 0xffu;
+    const float lx = xy.x - hx - tile_x0, ux = xy.x + hx - tile_x0;
+    const float ly = xy.y - hy - tile_y0, uy = xy.y + hy - tile_y0;
+    uint32_t col = 0, mask = 0;
+    col |= (ux >= 0.0f && lx <= 7.0f) ? 1u : 0u;
+    col |= (ux >= 8.0f && lx <= 15.0f) ? 2u : 0u;
+#pragma unroll
+    for (int sy = 0; sy < 4; ++sy)
+        if (uy >= 4.0f * sy && ly <= 4.0f * sy + 3.0f) mask |= col << (2 * sy);
+    return mask;
+}
+
 __global__ void __launch_bounds__(kBlock)
 render_global_fwd_kernel(Frame f, RenderArgs a) {
     __shared__ float2 s_xy[kBlock];
     __shared__ float4 s_co[kBlock];
     __shared__ float s_rgb[3][kBlock];
+    __shared__ uint32_t s_mask[kBlock];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
-    const uint32_t px = tile_x * kTile + (tid & 15), py = tile_y * kTile + (tid >> 4);
+    const uint32_t px = tile_x * kTile + (warp & 1) * 8 + (lane & 7), py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < (uint32_t)f.W && py < (uint32_t)f.H;
     const uint32_t pix_id = (uint32_t)f.W * py + px;
     const float pxf = (float)px, pyf = (float)py;
+    const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
 
     const uint2 range = a.ranges[tile_y * f.grid_x + tile_x];
     int todo = (int)(range.y - range.x);
@@ -43,40 +77,51 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
     bool done = !inside;
     float T = 1.0f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0;
 
     for (int r = 0; r < rounds; ++r, todo -= kBlock) {
         if (__syncthreads_count(done) == kBlock) break;
         const uint32_t src = range.x + r * kBlock + tid;
+        uint32_t mask = 0;
         if (src < range.y) {
             const uint32_t id = a.point_list[src];
-            s_xy[tid] = a.means2D[id];
-            s_co[tid] = a.conic_opacity[id];
+            const float2 xy = a.means2D[id];
+            const float4 co = a.conic_opacity[id];
+            s_xy[tid] = xy;
+            s_co[tid] = co;
             s_rgb[0][tid] = a.colors[3 * id + 0];
             s_rgb[1][tid] = a.colors[3 * id + 1];
             s_rgb[2][tid] = a.colors[3 * id + 2];
+            mask = strip_mask(xy, co, tile_x0, tile_y0);
         }
+        s_mask[tid] = mask;
         __syncthreads();
         const int n = min(kBlock, todo);
-        for (int j = 0; !done && j < n; ++j) {
-            ++contributor;
-            const float2 xy = s_xy[j];
-            const float4 co = s_co[j];
-            const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
-            const float power = gaussian_power(dx, dy, co.x, co.y, co.z);
-            if (power > 0.0f) continue;
-            const float alpha = fminf(0.99f, fmul(co.w, expf(power)));
-            if (alpha < kAlphaThreshold) continue;
-            const float test_T = fmul(T, fsub(1.0f, alpha));
-            if (test_T < kTThreshold) {
-                done = true;
-                continue;
+        for (int c = 0; c * 32 < n; ++c) {
+            if (__all_sync(0xffffffffu, done)) break;
+            uint32_t m = __ballot_sync(0xffffffffu, (s_mask[c * 32 + lane] >> warp) & 1u);
+            while (m) {
+                const int j = c * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                if (done) continue;
+                const float2 xy = s_xy[j];
+                const float4 co = s_co[j];
+                const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
+                const float power = gaussian_power(dx, dy, co.x, co.y, co.z);
+                if (power > 0.0f) continue;
+                const float alpha = fminf(0.99f, fmul(co.w, expf(power)));
+                if (alpha < kAlphaThreshold) continue;
+                const float test_T = fmul(T, fsub(1.0f, alpha));
+                if (test_T < kTThreshold) {
+                    done = true;
+                    continue;
+                }
+                C0 = ffma(T, fmul(alpha, s_rgb[0][j]), C0);
+                C1 = ffma(T, fmul(alpha, s_rgb[1][j]), C1);
+                C2 = ffma(T, fmul(alpha, s_rgb[2][j]), C2);
+                T = test_T;
+                last_contributor = (uint32_t)(r * kBlock + j + 1);
             }
-            C0 = ffma(T, fmul(alpha, s_rgb[0][j]), C0);
-            C1 = ffma(T, fmul(alpha, s_rgb[1][j]), C1);
-            C2 = ffma(T, fmul(alpha, s_rgb[2][j]), C2);
-            T = test_T;
-            last_contributor = contributor;
         }
     }
 
@@ -90,10 +135,47 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
     }
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
+// Sum v[0..8] over the 32 lanes with a recursive-halving exchange: after the five steps the total of
+// term k sits in lane kTermLane(k).  16 shuffles instead of 9 x 5.
+__device__ __forceinline__ float reduce9(float (&v)[9], int lane) {
+    // step 1 (xor 16): lower half keeps terms 0..7, upper half keeps term 8
+    const bool up16 = lane & 16;
+    float w[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int i = 0; i < 8; ++i) {
+        const float send = up16 ? v[i] : ((i == 0) ? v[8] : 0.0f);
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        w[i] = (up16 ? ((i == 0) ? v[8] : 0.0f) : v[i]) + recv;
+    }
+    // lower half: w[0..7] = terms 0..7 ; upper half: w[0] = term 8, w[1..7] = 0
+    // step 2 (xor 8): keep 4 of 8
+    const bool up8 = lane & 8;
+    float x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float recv = __shfl_xor_sync(0xffffffffu, up8 ? w[i] : w[4 + i], 8);
+        x[i] = (up8 ? w[4 + i] : w[i]) + recv;
+    }
+    // step 3 (xor 4): keep 2 of 4
+    const bool up4 = lane & 4;
+    float y[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float recv = __shfl_xor_sync(0xffffffffu, up4 ? x[i] : x[2 + i], 4);
+        y[i] = (up4 ? x[2 + i] : x[i]) + recv;
+    }
+    // step 4 (xor 2): keep 1 of 2
+    const bool up2 = lane & 2;
+    const float recv2 = __shfl_xor_sync(0xffffffffu, up2 ? y[0] : y[1], 2);
+    float z = (up2 ? y[1] : y[0]) + recv2;
+    // step 5 (xor 1): both lanes of a pair end with the total
+    z += __shfl_xor_sync(0xffffffffu, z, 1);
+    return z;
+}
+// term index whose total lane `lane` holds after reduce9 (lanes 16..31 hold term 8 in the lanes with bits 8,4,2 clear)
+__device__ __forceinline__ int term_of_lane(int lane) {
+    if (lane & 16) return ((lane & 14) == 0) ? 8 : -1;
+    return ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -102,23 +184,27 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
     __shared__ float2 s_xy[kBlock];
     __shared__ float4 s_co[kBlock];
     __shared__ float s_rgb[3][kBlock];
+    __shared__ uint32_t s_mask[kBlock];
     __shared__ float s_acc[9][kBlock];  // per-slab gradient accumulators
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
-    const uint32_t px = tile_x * kTile + (tid & 15), py = tile_y * kTile + (tid >> 4);
+    const uint32_t px = tile_x * kTile + (warp & 1) * 8 + (lane & 7), py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < (uint32_t)f.W && py < (uint32_t)f.H;
     const uint32_t pix_id = (uint32_t)f.W * py + px;
     const float pxf = (float)px, pyf = (float)py;
+    const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
 
     const uint2 range = a.ranges[tile_y * f.grid_x + tile_x];
     int todo = (int)(range.y - range.x);
+    const int total = todo;
     const int rounds = (todo + kBlock - 1) / kBlock;
 
     const float T_final = inside ? a.final_T[pix_id] : 0.f;
     float T = T_final;
-    uint32_t contributor = (uint32_t)todo;
     const uint32_t last_contributor = inside ? a.n_contrib[pix_id] : 0u;
+    // nothing behind the last contributor of any pixel of the tile can receive a gradient
+    const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
 
     const size_t plane = (size_t)f.W * f.H;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -131,80 +217,90 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
     const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
+    const int my_term = term_of_lane(lane);
 
     for (int r = 0; r < rounds; ++r, todo -= kBlock) {
         __syncthreads();
+        // slab r holds list positions total-1-(r*256+t), t = 0..255 (back to front)
         const int progress = r * kBlock + tid;
+        uint32_t mask = 0;
         if (range.x + progress < range.y) {
             const uint32_t id = a.point_list[range.y - progress - 1];
+            const float2 xy = a.means2D[id];
+            const float4 co = a.conic_opacity[id];
             s_id[tid] = id;
-            s_xy[tid] = a.means2D[id];
-            s_co[tid] = a.conic_opacity[id];
+            s_xy[tid] = xy;
+            s_co[tid] = co;
             s_rgb[0][tid] = a.colors[3 * id + 0];
             s_rgb[1][tid] = a.colors[3 * id + 1];
             s_rgb[2][tid] = a.colors[3 * id + 2];
+            mask = strip_mask(xy, co, tile_x0, tile_y0);
         }
+        s_mask[tid] = mask;
 #pragma unroll
         for (int k = 0; k < 9; ++k) s_acc[k][tid] = 0.f;
         __syncthreads();
         const int n = min(kBlock, todo);
-        for (int j = 0; j < n; ++j) {
-            --contributor;
-            bool hit = inside && contributor < last_contributor;
-            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
-            float4 co = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (hit) {
-                const float2 xy = s_xy[j];
-                co = s_co[j];
-                dx = fsub(xy.x, pxf);
-                dy = fsub(xy.y, pyf);
-                const float power = gaussian_power(dx, dy, co.x, co.y, co.z);
-                hit = !(power > 0.0f);
+        for (int c = 0; c * 32 < n; ++c) {
+            // list position (0-based) of entry j of this slab: total-1-(r*256+j); it contributes to a pixel iff
+            // position < last_contributor of that pixel
+            const int pos_first = total - 1 - (r * kBlock + c * 32);
+            if (pos_first - 31 >= (int)warp_last) continue;  // the whole chunk lies behind every pixel's last contributor
+            uint32_t m = __ballot_sync(0xffffffffu, (s_mask[c * 32 + lane] >> warp) & 1u);
+            while (m) {
+                const int j = c * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t contributor = (uint32_t)(total - 1 - (r * kBlock + j));
+                bool hit = inside && contributor < last_contributor;
+                float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+                float4 co = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (hit) {
-                    G = expf(power);
-                    alpha = fminf(0.99f, fmul(co.w, G));
-                    hit = !(alpha < kAlphaThreshold);
+                    const float2 xy = s_xy[j];
+                    co = s_co[j];
+                    dx = fsub(xy.x, pxf);
+                    dy = fsub(xy.y, pyf);
+                    const float power = gaussian_power(dx, dy, co.x, co.y, co.z);
+                    hit = !(power > 0.0f);
+                    if (hit) {
+                        G = expf(power);
+                        alpha = fminf(0.99f, fmul(co.w, G));
+                        hit = !(alpha < kAlphaThreshold);
+                    }
                 }
-            }
-            if (!__any_sync(0xffffffffu, hit)) continue;
-            float v[9];
+                if (!__any_sync(0xffffffffu, hit)) continue;
+                float v[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) v[k] = 0.f;
-            if (hit) {
-                T = T / (1.f - alpha);
-                const float dchannel_dcolor = alpha * T;
-                const float c0 = s_rgb[0][j], c1 = s_rgb[1][j], c2 = s_rgb[2][j];
-                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-                lc0 = c0;
-                lc1 = c1;
-                lc2 = c2;
-                float dL_dalpha = (c0 - acc0) * g0 + (c1 - acc1) * g1 + (c2 - acc2) * g2;
-                v[0] = dchannel_dcolor * g0;
-                v[1] = dchannel_dcolor * g1;
-                v[2] = dchannel_dcolor * g2;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                const float dL_dG = co.w * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * co.x - gdy * co.y;
-                const float dG_ddely = -gdy * co.z - gdx * co.y;
-                v[3] = dL_dG * dG_ddelx * ddelx_dx;
-                v[4] = dL_dG * dG_ddely * ddely_dy;
-                v[5] = -0.5f * gdx * dx * dL_dG;
-                v[6] = -0.5f * gdx * dy * dL_dG;
-                v[7] = -0.5f * gdy * dy * dL_dG;
-                v[8] = G * dL_dalpha;
-            }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) v[k] = warp_sum(v[k]);
-            if (lane < 9) {
-                float mine = v[0];
-#pragma unroll
-                for (int k = 1; k < 9; ++k) mine = (lane == k) ? v[k] : mine;
-                atomicAdd(&s_acc[lane][j], mine);
+                for (int k = 0; k < 9; ++k) v[k] = 0.f;
+                if (hit) {
+                    T = T / (1.f - alpha);
+                    const float dchannel_dcolor = alpha * T;
+                    const float c0 = s_rgb[0][j], c1 = s_rgb[1][j], c2 = s_rgb[2][j];
+                    acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+                    acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+                    acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                    lc0 = c0;
+                    lc1 = c1;
+                    lc2 = c2;
+                    float dL_dalpha = (c0 - acc0) * g0 + (c1 - acc1) * g1 + (c2 - acc2) * g2;
+                    v[0] = dchannel_dcolor * g0;
+                    v[1] = dchannel_dcolor * g1;
+                    v[2] = dchannel_dcolor * g2;
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    const float dL_dG = co.w * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * co.x - gdy * co.y;
+                    const float dG_ddely = -gdy * co.z - gdx * co.y;
+                    v[3] = dL_dG * dG_ddelx * ddelx_dx;
+                    v[4] = dL_dG * dG_ddely * ddely_dy;
+                    v[5] = -0.5f * gdx * dx * dL_dG;
+                    v[6] = -0.5f * gdx * dy * dL_dG;
+                    v[7] = -0.5f * gdy * dy * dL_dG;
+                    v[8] = G * dL_dalpha;
+                }
+                const float tot = reduce9(v, lane);
+                if (my_term >= 0 && !(lane & 1)) atomicAdd(&s_acc[my_term][j], tot);
             }
         }
         __syncthreads();
