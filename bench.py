@@ -55,7 +55,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -81,7 +84,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -152,7 +155,7 @@ def cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, repeats):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
@@ -292,6 +295,8 @@ def main():
 
     # ---- timed regions --------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: nvidia-smi's start-up cost stays outside the timed region
     if a.impl == "ours":
         _C.timing_reset()
         for _ in range(a.warmup):
@@ -300,7 +305,7 @@ def main():
         _C.timing_reset()
         launches0 = _C.kernel_launches()
     if rank == 0:
-        sampler.start()
+        sampler.mark()  # only samples taken from here on (= during the timed region) are reported
     ms_total = event_time_ms(step_resident, a.steps, a.warmup if a.impl != "ours" else 0, world)
     if a.impl == "ours":
         launches = _C.kernel_launches() - launches0

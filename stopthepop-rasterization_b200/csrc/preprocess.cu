@@ -78,6 +78,43 @@ __device__ __forceinline__ bool tile_contributes(float A, float B, float C, floa
     return p <= thr;
 }
 
+// The 32 coefficient rows of a warp are one contiguous span of rows*n_sh floats: stream it with 128-bit
+// loads (several independent loads in flight per lane) into the warp's shared-memory rows, skipping
+// quads whose rows were all culled.  NSH != 0 = compile-time row length (48 at SH degree 3).
+template <int NSH>
+__device__ __forceinline__ void stage_sh_rows(const float* __restrict__ wsrc, int rows, int n_sh_rt, uint32_t surv, int lane,
+                                              float* __restrict__ my_rows, int stride) {
+    const int n_sh = NSH ? NSH : n_sh_rt;
+    const int total = rows * n_sh;  // floats
+    const float4* __restrict__ src4 = reinterpret_cast<const float4*>(wsrc);
+#pragma unroll 4
+    for (int i = lane; 4 * i < total; i += 32) {
+        const int f0 = 4 * i, f3 = min(f0 + 3, total - 1);
+        const int r0 = f0 / n_sh, r3 = f3 / n_sh;
+        if (((surv >> r0) | (surv >> r3)) & 1u) {
+            float4 v;
+            if (f0 + 3 < total) {
+                v = __ldg(src4 + i);
+            } else {
+                v.x = __ldg(wsrc + f0);
+                v.y = (f0 + 1 < total) ? __ldg(wsrc + f0 + 1) : 0.f;
+                v.z = (f0 + 2 < total) ? __ldg(wsrc + f0 + 2) : 0.f;
+                v.w = 0.f;
+            }
+            const float e[4] = {v.x, v.y, v.z, v.w};
+            int row = r0, col = f0 - r0 * n_sh;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (f0 + k < total) my_rows[row * stride + col] = e[k];
+                if (++col == n_sh) {
+                    col = 0;
+                    ++row;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 template <bool TBC>
@@ -104,10 +141,22 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g) {
     float radius = 0.f, thr = 0.f;
     TileRect rc{0, 0, 0, 0};
 
+    // all per-Gaussian inputs are requested up front (independent loads in flight) although culled
+    // Gaussians will not use them: the kernel is latency-, not bandwidth-limited
+    float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s_in[3] = {0.f, 0.f, 0.f};
+    float opacity_in = 0.f;
     if (valid) {
-        x = a.means3D[3 * idx + 0];
-        y = a.means3D[3 * idx + 1];
-        z = a.means3D[3 * idx + 2];
+        x = __ldg(a.means3D + 3 * idx + 0);
+        y = __ldg(a.means3D + 3 * idx + 1);
+        z = __ldg(a.means3D + 3 * idx + 2);
+        opacity_in = __ldg(a.opacities + idx);
+        if (a.cov3D_precomp == nullptr) {
+            q_in = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+            s_in[0] = __ldg(a.scales + 3 * idx + 0);
+            s_in[1] = __ldg(a.scales + 3 * idx + 1);
+            s_in[2] = __ldg(a.scales + 3 * idx + 2);
+        }
         pv = view_transform(f.viewmatrix, x, y, z);
         if (pv.z <= kNearPlane) {  // in_frustum, auxiliary.h:223
             alive = false;
@@ -121,9 +170,9 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) cov6[k] = a.cov3D_precomp[6 * idx + k];
         } else {
-            const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+            const float4 q = q_in;
             const Rot3 R = quat_to_rot(q.x, q.y, q.z, q.w);
-            const float sx = a.scales[3 * idx + 0], sy = a.scales[3 * idx + 1], sz = a.scales[3 * idx + 2];
+            const float sx = s_in[0], sy = s_in[1], sz = s_in[2];
             gram_scaled_rot(R, fmul(a.scale_modifier, sx), fmul(a.scale_modifier, sy), fmul(a.scale_modifier, sz), cov6);
 #pragma unroll
             for (int k = 0; k < 6; ++k) g.cov3D[6 * idx + k] = cov6[k];
@@ -145,7 +194,7 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g) {
             co.x = fmul(cc, det_inv);
             co.y = fmul(cb, -det_inv);
             co.z = fmul(ca, det_inv);
-            co.w = fmul(a.opacities[idx], scaling);
+            co.w = fmul(opacity_in, scaling);
             if (co.w < kAlphaThreshold) alive = false;
         }
         if (alive) {
@@ -204,11 +253,20 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g) {
         uint32_t surv = __ballot_sync(0xffffffffu, alive);
         const int warp_base = (int)bid * kPreprocessThreads + warp * 32;
         const int n_sh = a.M * 3;
-        while (surv) {
-            const int r = __ffs(surv) - 1;
-            surv &= surv - 1;
-            const float* __restrict__ src = a.shs + (size_t)(warp_base + r) * n_sh;
-            for (int k = lane; k < n_sh; k += 32) my_rows[r * stride + k] = __ldg(src + k);
+        const float* __restrict__ wsrc = a.shs + (size_t)warp_base * n_sh;
+        const int rows = min(32, a.P - warp_base);
+        if (rows > 0 && (reinterpret_cast<uintptr_t>(wsrc) & 15u) == 0 && surv != 0) {
+            if (n_sh == 48)
+                stage_sh_rows<48>(wsrc, rows, 48, surv, lane, my_rows, stride);
+            else
+                stage_sh_rows<0>(wsrc, rows, n_sh, surv, lane, my_rows, stride);
+        } else {
+            while (surv) {
+                const int r = __ffs(surv) - 1;
+                surv &= surv - 1;
+                const float* __restrict__ src = a.shs + (size_t)(warp_base + r) * n_sh;
+                for (int k = lane; k < n_sh; k += 32) my_rows[r * stride + k] = __ldg(src + k);
+            }
         }
         __syncwarp();
         if (alive) {
@@ -228,9 +286,9 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g) {
         const float vx = fsub(f.cam_pos[0], x), vy = fsub(f.cam_pos[1], y), vz = fsub(f.cam_pos[2], z);
         if (g.cov3D_inv != nullptr) {
             // computeInvCov3D + packing, stopthepop_common.cuh:13-41, forward.cu:208-220
-            const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+            const float4 q = q_in;
             const Rot3 R = quat_to_rot(q.x, q.y, q.z, q.w);
-            const float sx = a.scales[3 * idx + 0], sy = a.scales[3 * idx + 1], sz = a.scales[3 * idx + 2];
+            const float sx = s_in[0], sy = s_in[1], sz = s_in[2];
             float ic[6];
             gram_scaled_rot(R, fdiv(1.0f, fmul(a.scale_modifier, fmaxf(1e-3f, sx))),
                             fdiv(1.0f, fmul(a.scale_modifier, fmaxf(1e-3f, sy))),

@@ -27,10 +27,84 @@ __device__ __forceinline__ F3 operator*(float s, F3 v) { return {s * v.x, s * v.
 __device__ __forceinline__ F3 operator+(F3 a, F3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 __device__ __forceinline__ float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
+// The 32 SH rows of a warp (and their gradient rows) are one contiguous span: they are moved between
+// global and shared memory with 128-bit, fully coalesced accesses; each lane then works on "its" row
+// in shared memory (row stride n_sh+1 floats: conflict-free).  The reference reads and writes the 48
+// coefficients per thread with a 192-byte stride (backward.cu:22-141).
+__device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, const Frame& f, int idx, float* __restrict__ row);
+
+template <bool STORE>
+__device__ __forceinline__ void move_sh_rows(float* __restrict__ gptr, int rows, int n_sh, uint32_t live, int lane,
+                                             float* __restrict__ my_rows, int stride) {
+    const int total = rows * n_sh;
+    float4* __restrict__ g4 = reinterpret_cast<float4*>(gptr);
+    const bool fast = n_sh == 48;
+#pragma unroll 4
+    for (int i = lane; 4 * i < total; i += 32) {
+        const int f0 = 4 * i, f3 = min(f0 + 3, total - 1);
+        const int r0 = fast ? (i / 12) : (f0 / n_sh), r3 = fast ? r0 : (f3 / n_sh);
+        if (!(((live >> r0) | (live >> r3)) & 1u)) continue;
+        int row = r0, col = f0 - r0 * n_sh;
+        if (f0 + 3 < total && (fast || r0 == r3)) {
+            if constexpr (STORE) {
+                float4 v;
+                v.x = my_rows[row * stride + col];
+                v.y = my_rows[row * stride + col + 1];
+                v.z = my_rows[row * stride + col + 2];
+                v.w = my_rows[row * stride + col + 3];
+                g4[i] = v;
+            } else {
+                const float4 v = __ldg(g4 + i);
+                my_rows[row * stride + col] = v.x;
+                my_rows[row * stride + col + 1] = v.y;
+                my_rows[row * stride + col + 2] = v.z;
+                my_rows[row * stride + col + 3] = v.w;
+            }
+        } else {
+            for (int k = 0; k < 4 && f0 + k < total; ++k) {
+                if ((live >> row) & 1u) {
+                    if constexpr (STORE) gptr[f0 + k] = my_rows[row * stride + col];
+                    else my_rows[row * stride + col] = __ldg(gptr + f0 + k);
+                }
+                if (++col == n_sh) {
+                    col = 0;
+                    ++row;
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
+    extern __shared__ float s_rows[];  // [8 warps][32 rows][3M+1]
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.P || !(a.radii[idx] > 0)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool alive = idx < a.P && a.radii[idx] > 0;
+    const uint32_t live = __ballot_sync(0xffffffffu, alive);
+    if (live == 0) return;
+    const int n_sh = a.M * 3, sh_stride = n_sh + 1;
+    float* const my_rows = s_rows + (size_t)warp * 32 * sh_stride;
+    const int warp_base = blockIdx.x * blockDim.x + warp * 32;
+    const bool sh_staged = a.shs != nullptr && n_sh > 0 &&
+                           ((reinterpret_cast<uintptr_t>(a.shs + (size_t)warp_base * n_sh) |
+                             reinterpret_cast<uintptr_t>(a.dL_dsh + (size_t)warp_base * n_sh)) & 15u) == 0;
+    if (sh_staged) {
+        move_sh_rows<false>(const_cast<float*>(a.shs) + (size_t)warp_base * n_sh, min(32, a.P - warp_base), n_sh, live, lane,
+                            my_rows, sh_stride);
+        __syncwarp();
+    }
+    if (alive) preprocess_bwd_one(a, f, idx, sh_staged ? my_rows + lane * sh_stride : nullptr);
+    if (sh_staged) {
+        __syncwarp();
+        move_sh_rows<true>(a.dL_dsh + (size_t)warp_base * n_sh, min(32, a.P - warp_base), n_sh, live, lane, my_rows,
+                           sh_stride);
+    }
+}
+
+// everything of one Gaussian; `row` = its SH coefficients in shared memory (overwritten with dL_dsh), or nullptr to
+// read/write global memory directly
+__device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, const Frame& f, int idx, float* __restrict__ row) {
     const float* __restrict__ vm = f.viewmatrix;
     const float* __restrict__ proj = f.projmatrix;
 
@@ -151,28 +225,30 @@ preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
         const F3 dir_orig = {mean.x - f.cam_pos[0], mean.y - f.cam_pos[1], mean.z - f.cam_pos[2]};
         const float len = sqrtf(dot(dir_orig, dir_orig));
         const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-        const float* __restrict__ shp = a.shs + (size_t)idx * a.M * 3;
-        float* __restrict__ dsh = a.dL_dsh + (size_t)idx * a.M * 3;
+        const float* __restrict__ shp = row ? row : a.shs + (size_t)idx * a.M * 3;
+        float* __restrict__ dsh = row ? row : a.dL_dsh + (size_t)idx * a.M * 3;
+        const int D = a.D;
         auto sh = [&](int k) { return F3{shp[3 * k], shp[3 * k + 1], shp[3 * k + 2]}; };
         F3 dRGB = {a.dL_dcolor[3 * idx], a.dL_dcolor[3 * idx + 1], a.dL_dcolor[3 * idx + 2]};
         dRGB.x *= a.clamped[3 * idx + 0] ? 0.f : 1.f;
         dRGB.y *= a.clamped[3 * idx + 1] ? 0.f : 1.f;
         dRGB.z *= a.clamped[3 * idx + 2] ? 0.f : 1.f;
-        auto put = [&](int k, float w) {
-            dsh[3 * k] = w * dRGB.x;
-            dsh[3 * k + 1] = w * dRGB.y;
-            dsh[3 * k + 2] = w * dRGB.z;
-        };
+        // weights of dL_dsh[k] = w[k] * dRGB; written after every coefficient has been read (the row is
+        // updated in place when it lives in shared memory)
+        float wk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) wk[k] = 0.f;
+        auto put = [&](int k, float w) { wk[k] = w; };
         F3 dx = {0, 0, 0}, dy = {0, 0, 0}, dz = {0, 0, 0};
         put(0, SH_C0);
-        if (a.D > 0) {
+        if (D > 0) {
             put(1, -SH_C1 * y);
             put(2, SH_C1 * z);
             put(3, -SH_C1 * x);
             dx = -SH_C1 * sh(3);
             dy = -SH_C1 * sh(1);
             dz = SH_C1 * sh(2);
-            if (a.D > 1) {
+            if (D > 1) {
                 const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
                 put(4, SH_C2[0] * xy);
                 put(5, SH_C2[1] * yz);
@@ -182,7 +258,7 @@ preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
                 dx = dx + (SH_C2[0] * y) * sh(4) + (SH_C2[2] * 2.f * -x) * sh(6) + (SH_C2[3] * z) * sh(7) + (SH_C2[4] * 2.f * x) * sh(8);
                 dy = dy + (SH_C2[0] * x) * sh(4) + (SH_C2[1] * z) * sh(5) + (SH_C2[2] * 2.f * -y) * sh(6) + (SH_C2[4] * 2.f * -y) * sh(8);
                 dz = dz + (SH_C2[1] * y) * sh(5) + (SH_C2[2] * 2.f * 2.f * z) * sh(6) + (SH_C2[3] * x) * sh(7);
-                if (a.D > 2) {
+                if (D > 2) {
                     put(9, SH_C3[0] * y * (3.f * xx - yy));
                     put(10, SH_C3[1] * xy * z);
                     put(11, SH_C3[2] * y * (4.f * zz - xx - yy));
@@ -199,6 +275,19 @@ preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
                     dz = dz + (SH_C3[1] * xy) * sh(10) + (SH_C3[2] * 4.f * 2.f * yz) * sh(11) +
                          (SH_C3[3] * 3.f * (2.f * zz - xx - yy)) * sh(12) + (SH_C3[4] * 4.f * 2.f * xz) * sh(13) +
                          (SH_C3[5] * (xx - yy)) * sh(14);
+                }
+            }
+        }
+        {
+            // direct path: only the active coefficients are written (the rest stays at the caller's zeros);
+            // staged path: the whole row is rewritten
+            const int ncoef = row ? a.M : min(a.M, (D + 1) * (D + 1));
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < ncoef) {
+                    dsh[3 * k] = wk[k] * dRGB.x;
+                    dsh[3 * k + 1] = wk[k] * dRGB.y;
+                    dsh[3 * k + 2] = wk[k] * dRGB.z;
                 }
             }
         }
@@ -270,7 +359,9 @@ preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
 }  // namespace
 
 cudaError_t launch_preprocess_bwd(const PreprocessBwdArgs& a, const Frame& f, cudaStream_t stream) {
-    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a, f);
+    const size_t smem = (a.shs != nullptr && a.M > 0) ? sizeof(float) * 8 * 32 * (a.M * 3 + 1) : 0;
+    cudaFuncSetAttribute(preprocess_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, smem, stream>>>(a, f);
     return cudaGetLastError();
 }
 

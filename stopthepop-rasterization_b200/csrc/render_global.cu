@@ -185,7 +185,7 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
     __shared__ float4 s_co[kBlock];
     __shared__ float s_rgb[3][kBlock];
     __shared__ uint32_t s_mask[kBlock];
-    __shared__ float s_acc[9][kBlock];  // per-slab gradient accumulators
+    __shared__ float s_acc[kBlock][9];  // per-slab gradient accumulators (stride 9: the nine terms of one entry hit nine banks)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
@@ -238,7 +238,7 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
         }
         s_mask[tid] = mask;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) s_acc[k][tid] = 0.f;
+        for (int k = 0; k < 9; ++k) s_acc[tid][k] = 0.f;
         __syncthreads();
         const int n = min(kBlock, todo);
         for (int c = 0; c * 32 < n; ++c) {
@@ -300,24 +300,24 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
                     v[8] = G * dL_dalpha;
                 }
                 const float tot = reduce9(v, lane);
-                if (my_term >= 0 && !(lane & 1)) atomicAdd(&s_acc[my_term][j], tot);
+                if (my_term >= 0 && !(lane & 1)) atomicAdd(&s_acc[j][my_term], tot);
             }
         }
         __syncthreads();
         if (tid < n) {
             const uint32_t id = s_id[tid];
-            const float c0 = s_acc[0][tid], c1 = s_acc[1][tid], c2 = s_acc[2][tid];
+            const float c0 = s_acc[tid][0], c1 = s_acc[tid][1], c2 = s_acc[tid][2];
             if (c0 != 0.f) atomicAdd(&a.dL_dcolor[3 * id + 0], c0);
             if (c1 != 0.f) atomicAdd(&a.dL_dcolor[3 * id + 1], c1);
             if (c2 != 0.f) atomicAdd(&a.dL_dcolor[3 * id + 2], c2);
-            const float m0 = s_acc[3][tid], m1 = s_acc[4][tid];
+            const float m0 = s_acc[tid][3], m1 = s_acc[tid][4];
             if (m0 != 0.f) atomicAdd(&a.dL_dmean2D[3 * id + 0], m0);
             if (m1 != 0.f) atomicAdd(&a.dL_dmean2D[3 * id + 1], m1);
-            const float k0 = s_acc[5][tid], k1 = s_acc[6][tid], k2 = s_acc[7][tid];
+            const float k0 = s_acc[tid][5], k1 = s_acc[tid][6], k2 = s_acc[tid][7];
             if (k0 != 0.f) atomicAdd(&a.dL_dconic[4 * id + 0], k0);
             if (k1 != 0.f) atomicAdd(&a.dL_dconic[4 * id + 1], k1);
             if (k2 != 0.f) atomicAdd(&a.dL_dconic[4 * id + 3], k2);
-            const float o = s_acc[8][tid];
+            const float o = s_acc[tid][8];
             if (o != 0.f) atomicAdd(&a.dL_dopacity[id], o);
         }
     }
