@@ -24,11 +24,23 @@
 // The per-pixel arithmetic is the rounding-pinned sequence of stp_math.cuh.
 #include "stp_kernels.cuh"
 
+#ifndef STP_HIER_SPEC
+#define STP_HIER_SPEC 0
+#endif
+#ifndef STP_HIER_MIDBATCH
+#define STP_HIER_MIDBATCH 0
+#endif
+#ifndef STP_HIER_MINB
+#define STP_HIER_MINB 3
+#endif
+
 namespace stp {
 
 namespace {
 
 constexpr float kFltMax = 3.402823466e+38f;
+constexpr int kDeadBit = 0x40000000;  // entry cannot reach any pixel of the 4x4 block (ids are < 2^30)
+constexpr int kIdMask = 0x3fffffff;
 constexpr int kTailStride = 80;  // 64 entries + 16 pad: the two blocks of a warp live in disjoint banks
 
 template <int MID>
@@ -60,6 +72,19 @@ __device__ __forceinline__ void load_inv(const float4* __restrict__ inv, int id,
     ux = c.x; uy = c.y; uz = c.z;
 }
 
+// true if no pixel of the 4x4 block at (bx0,by0) can see alpha >= 1/255 from this Gaussian: real q(d) <= thr implies
+// |dx| <= sqrt(2 thr C/det), |dy| <= sqrt(2 thr A/det); thr inflated by 0.1 % + 0.01, half-widths by 0.01 px.
+__device__ __forceinline__ bool block_unreachable(float2 xy, float4 co, float bx0, float by0) {
+    const float det = co.x * co.z - co.y * co.y;
+    if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f) || !(co.w > 0.0f)) return false;
+    const float thr = __logf(255.0f * co.w) * 1.001f + 0.01f;
+    if (!(thr > 0.0f)) return false;
+    const float s = 2.0f * thr / det;
+    const float hx = sqrtf(s * co.z) * 1.0001f + 0.01f, hy = sqrtf(s * co.x) * 1.0001f + 0.01f;
+    if (!(hx < 1e9f) || !(hy < 1e9f)) return false;
+    return (xy.x + hx < bx0) || (xy.x - hx > bx0 + 3.0f) || (xy.y + hy < by0) || (xy.y - hy > by0 + 3.0f);
+}
+
 // per-pixel blending state
 template <bool BWD>
 struct PixelState;
@@ -74,7 +99,7 @@ struct PixelState<true> {
 };
 
 template <int HEAD, int MID, bool CULL, bool BWD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (HEAD <= 4 && MID <= 12) ? STP_HIER_MINB : 1)
 render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Sh = HierShared<MID>;
@@ -206,24 +231,32 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         hd[HEAD - 1] = kFltMax;
     };
 
-    // ---- one entry arrives at the pixel (front4OneFromMid inner body, :421-536) -----------------------------------------
-    auto head_push = [&](int id) {
-        if (hcount >= HEAD) blend_one();
-        if (id < 0 || !active) return;
-        // the cheap rejections first; both are side-effect free, so their order is irrelevant
+    // ---- an entry arrives at the pixel (front4OneFromMid inner body, :421-536) ---------------------------------------------
+    // Split in two so that the four entries a quad receives together can be evaluated with instruction-level
+    // parallelism: head_eval is side-effect free (alpha test first, then -- only for survivors -- the 48-byte
+    // inverse covariance and the depth on the pixel's ray); head_insert is the sequential queue update.
+    // Entries flagged kDeadBit cannot reach any pixel of this 4x4 block (conservative test at the tail stage):
+    // they still flow through every queue (they decide WHEN other entries are popped and blended) but are never
+    // evaluated per pixel.
+    auto head_eval = [&](int id, float& ed, float& es) -> bool {
+        if (id < 0 || (id & kDeadBit) || !active) return false;
         const float2 xy = __ldg(means2D + id);
         const float4 co = __ldg(conic_opacity + id);
         const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
         const float power = gaussian_power(dx, dy, co.x, co.y, co.z);
-        if (power > 0.0f) return;
+        if (power > 0.0f) return false;
         const float G = expf(power);
         const float alpha = fminf(0.99f, fmul(co.w, G));
-        if (alpha < kAlphaThreshold) return;
+        if (alpha < kAlphaThreshold) return false;
         float ic[6], ux, uy, uz;
         load_inv(cov3D_inv, id, ic, ux, uy, uz);
-        const float depth = depth_along_ray(ic, ux, uy, uz, ray);
-        if (depth < 0.0f) return;
-        float ed = depth, es = BWD ? G : alpha;
+        ed = depth_along_ray(ic, ux, uy, uz, ray);
+        es = BWD ? G : alpha;
+        return !(ed < 0.0f);
+    };
+    auto head_insert = [&](bool ok, int id, float ed, float es) {
+        if (hcount >= HEAD) blend_one();
+        if (!ok || !active) return;
         int ei = id;
 #pragma unroll
         for (int k = 0; k < HEAD; ++k) {
@@ -248,19 +281,53 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     auto quad_to_head = [&]() {
         const bool any = __any_sync(qmask, active);
         if (!any) return;
+        int ids[4];
+        float ed[4], es[4];
+        bool ok[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) head_push(oi[k]);
+        for (int k = 0; k < 4; ++k) ids[k] = oi[k];
+#if STP_HIER_SPEC
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ok[k] = head_eval(ids[k], ed[k], es[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) head_insert(ok[k], ids[k], ed[k], es[k]);
+#else
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (hcount >= HEAD) blend_one();
+            ok[k] = head_eval(ids[k], ed[k], es[k]);
+            if (ok[k]) {
+                float e_d = ed[k], e_s = es[k];
+                int ei = ids[k];
+#pragma unroll
+                for (int j = 0; j < HEAD; ++j) {
+                    if (e_d < hd[j]) {
+                        const float td = hd[j], ts = hs[j];
+                        const int ti = hi[j];
+                        hd[j] = e_d; hs[j] = e_s; hi[j] = ei;
+                        e_d = td; e_s = ts; ei = ti;
+                    }
+                }
+                ++hcount;
+            }
+        }
+#endif
     };
 
     // one group of 4 tail entries (ids g_id[0..3], quad lane p owns entry p) enters the mid queue (:566-677)
-    auto mid_push_group = [&](int my_id) {
+    // depth of one tail entry on the quad's ray (side-effect free: the four groups of a tail pop are evaluated
+    // together for instruction-level parallelism, then merged one after the other)
+    auto mid_depth = [&](int my_id) -> float {
         float my_d = kFltMax;
         if (my_id >= 0) {
             float ic[6], ux, uy, uz;
-            load_inv(cov3D_inv, my_id, ic, ux, uy, uz);
+            load_inv(cov3D_inv, my_id & kIdMask, ic, ux, uy, uz);
             const Vec3 mr{mrx, mry, mrz};
             my_d = depth_along_ray(ic, ux, uy, uz, mr);
         }
+        return my_d;
+    };
+    auto mid_push_group = [&](int my_id, float my_d) {
         // rank among the 4 new entries, ties by lane (shflRankingLocal, :129-143)
         float nd[4];
         int rank = 0;
@@ -345,6 +412,12 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
                     float ic[6], ux, uy, uz;
                     load_inv(cov3D_inv, id, ic, ux, uy, uz);
                     d = depth_along_ray(ic, ux, uy, uz, tray);
+                    if constexpr (!CULL) {
+                        // conservative "cannot reach this block" flag (bounding box of the alpha >= 1/255 ellipse,
+                        // inflated far beyond the rounding error of the per-pixel evaluation)
+                        if (block_unreachable(__ldg(means2D + id), __ldg(conic_opacity + id), (float)cx, (float)cy))
+                            id |= kDeadBit;
+                    }
                 } else {
                     id = -1;
                 }
@@ -409,8 +482,27 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
 #pragma unroll 1
         for (int rep = 0; rep < 2; ++rep) {
             if (tcount > 32) {
+#if !STP_HIER_MIDBATCH
 #pragma unroll 1
-                for (int g = 0; g < 4; ++g) mid_push_group(ti[tbase + 4 * g + p]);
+                for (int g = 0; g < 4; ++g) {
+                    const int id_g = ti[tbase + 4 * g + p];
+                    mid_push_group(id_g, mid_depth(id_g));
+                }
+#else
+                int gid[4];
+                float gd[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) gid[g] = ti[tbase + 4 * g + p];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) gd[g] = mid_depth(gid[g]);
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    // runtime-indexed pick without local memory
+                    const int id_g = g == 0 ? gid[0] : g == 1 ? gid[1] : g == 2 ? gid[2] : gid[3];
+                    const float d_g = g == 0 ? gd[0] : g == 1 ? gd[1] : g == 2 ? gd[2] : gd[3];
+                    mid_push_group(id_g, d_g);
+                }
+#endif
                 tbase += 16;
                 tcount -= 16;
             }
@@ -420,7 +512,8 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     // ---- drain: tail -> mid -> head (:855-925) ---------------------------------------------------------------------------
     if (__any_sync(hmask, active)) {
         while (tcount > 0) {
-            mid_push_group(p < tcount ? ti[tbase + p] : -1);
+            const int did = p < tcount ? ti[tbase + p] : -1;
+            mid_push_group(did, mid_depth(did));
             tbase += 4;
             tcount -= min(tcount, 4);
         }
