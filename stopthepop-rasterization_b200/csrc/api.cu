@@ -113,6 +113,7 @@ struct StageSample {
     std::vector<const char*> names;
 };
 thread_local std::vector<StageSample> g_pending;
+thread_local std::vector<cudaEvent_t> g_event_pool;  // resolved events are reused: cudaEventCreate costs microseconds
 constexpr size_t kMaxPending = 8192;
 
 struct StageTimer {
@@ -123,7 +124,12 @@ struct StageTimer {
     void mark(const char* name) {
         if (!on) return;
         cudaEvent_t e;
-        cudaEventCreate(&e);
+        if (!g_event_pool.empty()) {
+            e = g_event_pool.back();
+            g_event_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
         cudaEventRecord(e, stream);
         cur.ev.push_back(e);
         cur.names.push_back(name);
@@ -147,7 +153,7 @@ void resolve_sample(StageSample& smp, std::vector<std::pair<const char*, float>>
 }
 void destroy_pending() {
     for (auto& smp : g_pending)
-        for (auto e : smp.ev) cudaEventDestroy(e);
+        for (auto e : smp.ev) g_event_pool.push_back(e);
     g_pending.clear();
 }
 
