@@ -67,6 +67,11 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi takes a few hundred ms to attach to the driver and stalls kernel launches while it does:
+            # wait for its first sample so that this start-up never overlaps the warm-up or the timed region
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 10.0 and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -111,25 +116,47 @@ def algorithmic_bytes(P, V, R, N, T, M, s_flag, c_flag):
     }
 
 
-KERNEL_OF_STAGE = {"Preprocess": "preprocess_kernel", "Duplicate": "duplicate_kernel", "Sort": "radix sort + tile_ranges_kernel",
+KERNEL_OF_STAGE = {"Preprocess": "preprocess_kernel", "Duplicate": "duplicate_kernel", "Sort": "tile_sort_small_kernel + tile_sort_large_kernel",
                    "Render": "render_*_fwd_kernel", "RenderBackward": "render_*_bwd_kernel",
                    "PreprocessBackward": "preprocess_bwd_kernel"}
 
 
-def event_time_ms(fn, steps, warmup, world):
-    """W untimed warm-ups, then exactly K steps bracketed by barrier + synchronize; max over ranks."""
-    for _ in range(warmup):
+TRACE_STEPS = False
+MIN_WARM_S = 0.4  # the W warm-up steps are extended to at least this long (SM clocks ramp up from idle)
+STEP_TRACE = []  # --trace-steps: per-step event times of every timed region (diagnostics, adds one event per step)
+
+
+def event_time_ms(fn, steps, warmup, world, min_warm_s=0.0):
+    """W untimed warm-ups (and at least min_warm_s seconds of them, so that the SM clocks have ramped up from idle
+    before the timed region starts), then exactly K steps bracketed by barrier + synchronize; max over ranks."""
+    t0 = time.perf_counter()
+    n = 0
+    while n < warmup or time.perf_counter() - t0 < min_warm_s:
         fn()
+        n += 1
+        if n % 8 == 0:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    marks = []
     for _ in range(steps):
         fn()
+        if TRACE_STEPS:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
     e1.record()
     torch.cuda.synchronize()
+    if TRACE_STEPS:
+        prev, row = e0, []
+        for ev in marks:
+            row.append(round(prev.elapsed_time(ev), 3))
+            prev = ev
+        STEP_TRACE.append(row)
     if world > 1:
         dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -160,9 +187,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace-steps", action="store_true", help="diagnostics: per-step times of every timed region")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
+    global TRACE_STEPS
+    TRACE_STEPS = a.trace_steps
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -317,14 +347,21 @@ def main():
         sampler.start()  # before the warm-up: nvidia-smi's start-up cost stays outside the timed region
     if a.impl == "ours":
         _C.timing_reset()
-        for _ in range(a.warmup):
+        t_w = time.perf_counter()
+        n_w = 0
+        while n_w < a.warmup or time.perf_counter() - t_w < MIN_WARM_S:
             step_resident()
+            n_w += 1
+            if n_w % 8 == 0:
+                torch.cuda.synchronize()
+                _C.timing_reset()
         torch.cuda.synchronize()
         _C.timing_reset()
         launches0 = _C.kernel_launches()
     if rank == 0:
         sampler.mark()  # only samples taken from here on (= during the timed region) are reported
-    ms_total = event_time_ms(step_resident, a.steps, a.warmup if a.impl != "ours" else 0, world)
+    ms_total = event_time_ms(step_resident, a.steps, a.warmup if a.impl != "ours" else 0, world,
+                             MIN_WARM_S if a.impl != "ours" else 0.0)
     if a.impl == "ours":
         launches = _C.kernel_launches() - launches0
         stages = _C.timing_summary()
@@ -377,7 +414,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         per_stage = {k: {"ms": v[0], "GBps": ab[k] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None, "bytes": ab[k]}
                      for k, v in stages.items() if k in ab}
-        own = {k: v for k, v in per_stage.items() if k != "Sort"}  # the sort is a library call (CUB) in this round
+        own = per_stage
         dom = max(own, key=lambda k: own[k]["ms"])
         traffic = None
         try:
@@ -410,6 +447,8 @@ def main():
         line["cpu_baseline"] = {"value": e2e_value, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "reference",
                                 "sample": "unmodified reference CUDA build (oracle/_ref, sm_100) on the same GPU, full "
                                           "workload -- the reference ships no CPU path; host cores only launch kernels"}
+    if TRACE_STEPS:
+        line["step_trace_ms"] = STEP_TRACE
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -99,9 +99,10 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user,
 
 /* replaces: CudaRasterizer::Rasterizer::backward, rasterizer.h:222-257 (impl rasterizer_impl.cu:417-526)
  * as called by RasterizeGaussiansBackwardCUDA, rasterize_points.cu:141-232.
- * All dL_* outputs must be zero-filled by the caller (torch::zeros, rasterize_points.cu:178-186).
- *   dL_dmean2D [P,3], dL_dconic [P,2,2], dL_dopacity [P,1], dL_dcolor [P,3], dL_dmean3D [P,3],
- *   dL_dcov3D [P,6], dL_dsh [P,M,3], dL_dscale [P,3], dL_drot [P,4]
+ * The four atomically accumulated outputs dL_dmean2D [P,3], dL_dconic [P,2,2], dL_dopacity [P,1], dL_dcolor [P,3]
+ * must be zero-filled by the caller (torch::zeros, rasterize_points.cu:178-186).  dL_dmean3D [P,3], dL_dcov3D [P,6],
+ * dL_dsh [P,M,3], dL_dscale [P,3], dL_drot [P,4] may be uninitialised: every row is written (zeros for culled
+ * Gaussians), which removes 256 B/Gaussian of memset per iteration.
  */
 int stp_backward(int P, int D, int M, int R,
                  const float* background, int width, int height,
@@ -137,7 +138,6 @@ typedef struct StpGeometryView {
     float* conic_opacity;    /* [4P]  f32  conic (x,y,z) + opacity                     */
     float* rgb;              /* [3P]  f32  SH-evaluated colour                         */
     uint32_t* tiles_touched; /* [P]   u32                                              */
-    uint32_t* point_offsets; /* [P]   u32  inclusive prefix sum of tiles_touched       */
 } StpGeometryView;
 typedef struct StpBinningView {
     uint32_t* point_list;        /* [R] u32 sorted Gaussian ids (0xFFFFFFFF = padding)  */

@@ -214,7 +214,7 @@ int stp_requires_cov3D_inv(const StpSettings* s) {
 }
 
 size_t stp_geometry_bytes(int P, int inv) { return required<GeometryState>((size_t)P, inv != 0); }
-size_t stp_binning_bytes(int R) { return required<BinningState>((size_t)R, sort_temp_bytes((size_t)R)); }
+size_t stp_binning_bytes(int R) { return required<BinningState>((size_t)R); }
 size_t stp_image_bytes(int W, int H) {
     return required<ImageState>((size_t)W * H, (size_t)((W + 15) / 16) * ((H + 15) / 16));
 }
@@ -232,13 +232,12 @@ int stp_view_geometry(char* buf, int P, int inv, StpGeometryView* out) {
     out->conic_opacity = reinterpret_cast<float*>(g.conic_opacity);
     out->rgb = g.rgb;
     out->tiles_touched = g.tiles_touched;
-    out->point_offsets = g.point_offsets;
     return STP_OK;
 }
 int stp_view_binning(char* buf, int R, StpBinningView* out) {
     if (buf == nullptr || out == nullptr) return fail(STP_ERR_INVALID_ARGUMENT, "null argument");
     char* p = buf;
-    BinningState b = BinningState::from_chunk(p, (size_t)R, 0);
+    BinningState b = BinningState::from_chunk(p, (size_t)R);
     out->point_list = b.point_list;
     out->point_list_keys = b.keys;
     return STP_OK;
@@ -306,8 +305,9 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     pa.proper_ewa_scaling = s.proper_ewa_scaling;
     pa.prefiltered = prefiltered != 0;
     pa.radii = radii;
-    STP_CUDA(launch_preprocess(pa, f, g, s.tile_based_culling, stream), "preprocess");
-    g_launches += 1;
+    STP_CUDA(launch_preprocess(pa, f, g, img.tile_count, s.tile_based_culling, stream), "preprocess");
+    STP_CUDA(launch_tile_scan(f, g, img, stream), "tile scan");
+    g_launches += 2;
     timer.mark("Preprocess");
 
     uint32_t R = 0;
@@ -319,20 +319,19 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     }
     if (num_rendered_out) *num_rendered_out = (int)R;
 
-    const size_t sort_bytes = sort_temp_bytes((size_t)R);
-    char* bp = binning_alloc(binning_user, required<BinningState>((size_t)R, sort_bytes));
+    char* bp = binning_alloc(binning_user, required<BinningState>((size_t)R));
     if (!bp) return fail(STP_ERR_ALLOC, "binning arena allocation failed");
-    BinningState b = BinningState::from_chunk(bp, (size_t)R, sort_bytes);
+    BinningState b = BinningState::from_chunk(bp, (size_t)R);
 
     if (R > 0) {
-        STP_CUDA(launch_duplicate(P, f, s, g, radii, b.keys_unsorted, b.point_list_unsorted, stream), "duplicate");
+        STP_CUDA(launch_duplicate(P, f, s, g, radii, img, b, (size_t)R, stream), "duplicate");
         g_launches += 1;
     }
     timer.mark("Duplicate");
-    const int bit = (int)higher_msb((uint32_t)tiles);
-    STP_CUDA(launch_sort(b, (size_t)R, 32 + bit, stream), "sort");
-    STP_CUDA(launch_tile_ranges((size_t)R, b.keys, img.ranges, tiles, stream), "tile ranges");
-    g_launches += (R > 0) + sort_kernel_launches((size_t)R, 32 + bit);
+    if (R > 0) {
+        STP_CUDA(launch_tile_sort(f, g, img, b, stream), "tile sort");
+        g_launches += sort_kernel_launches();
+    }
     timer.mark("Sort");
 
     RenderArgs ra;
@@ -386,7 +385,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     char* gp = geom_buffer;
     GeometryState g = GeometryState::from_chunk(gp, (size_t)P, inv);
     char* bp = binning_buffer;
-    BinningState b = BinningState::from_chunk(bp, (size_t)R, 0);
+    BinningState b = BinningState::from_chunk(bp, (size_t)R);
     char* ip = image_buffer;
     ImageState img = ImageState::from_chunk(ip, (size_t)width * height, (size_t)tiles);
 

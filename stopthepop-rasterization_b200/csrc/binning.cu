@@ -1,26 +1,29 @@
-// binning.cu -- (tile | depth) key emission, device radix sort, per-tile ranges.
+// binning.cu -- tile binning and depth sort: per-tile buckets + one in-shared-memory sort per tile.
 //
 // Replaces: duplicateWithKeysCUDA (forward.cu:25-65), duplicateWithKeys_extended<TBC,LB,ORDER>
-// (stopthepop_common.cuh:324-621), cub::DeviceRadixSort::SortPairs (rasterizer_impl.cu:344-352),
+// (stopthepop_common.cuh:324-621), cub::DeviceRadixSort::SortPairs (rasterizer_impl.cu:344-352) and
 // identifyTileRanges (rasterizer_impl.cu:133-158).
 //
-// Key = (tile_id << 32) | float_bits(depth), value = Gaussian index, emitted row-major over the tile
-// rectangle, Gaussians in index order (offsets from the fused scan in preprocess.cu).  Only key
-// bits [0, 32+higher_msb(tiles)) take part in the sort; the sort is stable, so equal keys keep
-// ascending Gaussian index -- the order the reference's stable CUB sort produces.
+// The reference sorts all R (tile << 32 | depth bits) keys with a stable 6-pass LSD radix sort (152 B of HBM
+// traffic per instance) and then finds the tile boundaries.  The result of that sort is fully determined:
+// instances grouped by tile id, inside a tile ascending by the raw depth bits, ties in emission order =
+// ascending Gaussian index.  Here the same order is produced without any global sort pass:
+//   1. preprocess.cu histograms the instances per tile (it visits every (Gaussian, tile) pair anyway);
+//   2. tile_scan_kernel turns the histogram into bucket offsets -- these ARE the tile ranges;
+//   3. duplicate_kernel claims a slot in its tile's bucket per instance (atomic cursor) and stores one 8-byte
+//      record (depth bits << 32 | Gaussian index): unique per tile, so any comparison sort reproduces the
+//      stable order regardless of the (non-deterministic) slot order;
+//   4. tile_sort_* sorts every bucket in shared memory (bitonic network, warp-synchronous below 64-element
+//      span) and writes point_list and the sorted 64-bit keys.  Tiles longer than the largest shared-memory
+//      capacity are chunk-sorted and merged through a global ping-pong buffer (merge path).
+// HBM traffic: 8 B written + 8 B read + 12 B written per instance.
 #include "stp_kernels.cuh"
-#include "radix_sort.cuh"
 
 namespace stp {
 
 namespace {
 
 constexpr int kSeqTiles = 8;
-constexpr uint32_t kInvalidTile = 0xFFFFFFFFu;
-
-__device__ __forceinline__ uint64_t make_key(uint32_t tile, float depth) {
-    return ((uint64_t)tile << 32) | (uint64_t)__float_as_uint(depth);
-}
 
 struct DupGaussian {
     float2 xy;
@@ -30,7 +33,7 @@ struct DupGaussian {
     float depth;     // global depth (Z / DISTANCE)
     float thr;
     int x0, y0, w, n;  // rect origin, width, tile count
-    uint32_t off, off_end, idx;
+    uint32_t idx;
 };
 
 // evaluates one tile of one Gaussian: returns whether a key is emitted and its depth.
@@ -61,10 +64,16 @@ __device__ __forceinline__ bool eval_tile(const DupGaussian& gs, const RayCam& c
     return !TBC || power <= gs.thr;
 }
 
+__device__ __forceinline__ void emit_instance(uint32_t* __restrict__ cursor, uint64_t* __restrict__ bucket, uint32_t cap,
+                                              uint32_t tile_id, float depth, uint32_t idx) {
+    const uint32_t slot = atomicAdd(cursor + tile_id, 1u);
+    if (slot < cap) bucket[slot] = ((uint64_t)__float_as_uint(depth) << 32) | (uint64_t)idx;
+}
+
 template <bool TBC, int ORDER>
 __global__ void __launch_bounds__(256)
-duplicate_kernel(int P, Frame f, GeometryState g, const int* __restrict__ radii, uint64_t* __restrict__ keys,
-                 uint32_t* __restrict__ values) {
+duplicate_kernel(int P, Frame f, GeometryState g, const int* __restrict__ radii, uint32_t* __restrict__ cursor,
+                 uint64_t* __restrict__ bucket, uint32_t cap) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     constexpr bool NEED_CO = TBC || ORDER == 3;
@@ -77,7 +86,6 @@ duplicate_kernel(int P, Frame f, GeometryState g, const int* __restrict__ radii,
     gs.n = 0;
     gs.w = 1;
     gs.x0 = gs.y0 = 0;
-    gs.off = gs.off_end = 0;
     gs.idx = (uint32_t)idx;
     gs.thr = 0.f;
     gs.depth = 0.f;
@@ -89,8 +97,6 @@ duplicate_kernel(int P, Frame f, GeometryState g, const int* __restrict__ radii,
         gs.y0 = rc.y0;
         gs.w = max(rc.x1 - rc.x0, 1);
         gs.n = (rc.x1 - rc.x0) * (rc.y1 - rc.y0);
-        gs.off = (idx == 0) ? 0u : g.point_offsets[idx - 1];
-        gs.off_end = g.point_offsets[idx];
         gs.depth = g.depths[idx];
         if constexpr (NEED_CO) {
             gs.co = g.conic_opacity[idx];
@@ -105,17 +111,11 @@ duplicate_kernel(int P, Frame f, GeometryState g, const int* __restrict__ radii,
     }
 
     // sequential head of the rectangle
-    uint32_t off = gs.off;
     for (int t = 0; t < min(gs.n, kSeqTiles); ++t) {
         uint32_t tile_id;
         float depth;
-        if (eval_tile<TBC, ORDER>(gs, cam, t, (uint32_t)f.grid_x, tile_id, depth)) {
-            if (off < gs.off_end) {
-                keys[off] = make_key(tile_id, depth);
-                values[off] = gs.idx;
-            }
-            ++off;
-        }
+        if (eval_tile<TBC, ORDER>(gs, cam, t, (uint32_t)f.grid_x, tile_id, depth))
+            emit_instance(cursor, bucket, cap, tile_id, depth, gs.idx);
     }
 
     // warp-cooperative remainder
@@ -145,57 +145,276 @@ duplicate_kernel(int P, Frame f, GeometryState g, const int* __restrict__ radii,
         o.w = __shfl_sync(0xffffffffu, gs.w, src);
         o.n = __shfl_sync(0xffffffffu, gs.n, src);
         o.idx = __shfl_sync(0xffffffffu, gs.idx, src);
-        o.off_end = __shfl_sync(0xffffffffu, gs.off_end, src);
-        uint32_t o_off = __shfl_sync(0xffffffffu, off, src);
-        for (int base = kSeqTiles; base < o.n; base += 32) {
-            const int t = base + lane;
+        for (int t = kSeqTiles + lane; t < o.n; t += 32) {
             uint32_t tile_id = 0;
             float depth = 0.f;
-            const bool w = (t < o.n) && eval_tile<TBC, ORDER>(o, cam, t, (uint32_t)f.grid_x, tile_id, depth);
-            const uint32_t m = __ballot_sync(0xffffffffu, w);
-            const uint32_t pos = o_off + __popc(m & ((1u << lane) - 1u));
-            if (w && pos < o.off_end) {
-                keys[pos] = make_key(tile_id, depth);
-                values[pos] = o.idx;
-            }
-            o_off += __popc(m);
+            if (eval_tile<TBC, ORDER>(o, cam, t, (uint32_t)f.grid_x, tile_id, depth))
+                emit_instance(cursor, bucket, cap, tile_id, depth, o.idx);
         }
-        if (lane == src) off = o_off;
-    }
-
-    // shortfall padding (stopthepop_common.cuh:504-508,615-619): cannot happen while preprocess and
-    // duplicate share the same rounding-pinned tile test, kept for robustness.
-    for (; off < gs.off_end; ++off) {
-        keys[off] = make_key(kInvalidTile, 3.402823466e+38f);
-        values[off] = 0xFFFFFFFFu;
     }
 }
 
-// identifyTileRanges, rasterizer_impl.cu:133-158 (ranges pre-zeroed)
-__global__ void tile_ranges_kernel(uint32_t R, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t cur = (uint32_t)(keys[i] >> 32);
-    const bool valid = cur != kInvalidTile;
-    if (i == 0) {
-        if (valid) ranges[cur].x = 0;
+// ---- histogram -> bucket offsets = tile ranges (identifyTileRanges, rasterizer_impl.cu:133-158: tiles without
+// instances keep the (0,0) of the reference's memset) --------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kSmallCap = 2048;    // entries sorted by one 256-thread CTA in 16 KB of shared memory
+constexpr int kLargeCap = 16384;   // entries sorted by one 1024-thread CTA in 128 KB of shared memory
+constexpr int kLargeThreads = 1024;
+
+// CTA b owns tiles [b*1024, (b+1)*1024): it first sums every count before its segment (the whole histogram is a few
+// tens of KB in L2, so a redundant read is cheaper than any inter-CTA dependency), then scans its own segment.
+__global__ void __launch_bounds__(kScanThreads)
+tile_scan_kernel(int tiles, const uint32_t* __restrict__ count, uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
+                 uint32_t* __restrict__ large_tiles, uint32_t* __restrict__ counters) {
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    __shared__ uint32_t s_before;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int seg0 = blockIdx.x * kScanThreads;
+    uint32_t before = 0;
+    for (int t = tid; t < seg0; t += kScanThreads) before += count[t];
+    const int t = seg0 + tid;
+    const uint32_t c = t < tiles ? count[t] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    if (tid == 0) s_before = 0;
+    __syncthreads();
+    if (lane == 0 && before != 0) atomicAdd(&s_before, before);
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t end = s_before + s_warp[warp] + incl, start = end - c;
+    if (t < tiles) {
+        ranges[t] = c ? make_uint2(start, end) : make_uint2(0u, 0u);
+        cursor[t] = start;
+        if (c > (uint32_t)kSmallCap) large_tiles[atomicAdd(counters + 3, 1u)] = (uint32_t)t;
+        if (t == tiles - 1) counters[1] = end;  // R
+    }
+}
+
+// ---- bitonic sort of one bucket: n unique 64-bit records, virtually padded with ~0 to np (a power of two).
+// Every warp keeps a span of 32*E consecutive elements in registers (lane L holds elements L, L+32, ... of the span):
+// compare-exchange distances below 32 are warp shuffles, distances 32 .. 16*E are register-to-register, and only
+// distances of a whole span or more go through shared memory -- for a 512-entry tile 6 of the 45 stages.
+template <int E>
+__device__ __forceinline__ void reg_stage(uint64_t (&v)[E], int j, int k, int base, int lane) {
+    if (j >= 32) {
+        const int jj = j >> 5;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if ((e & jj) == 0) {
+                const bool up = ((base + e * 32 + lane) & k) == 0;
+                const uint64_t a = v[e], b = v[e | jj];
+                const bool sw = (a > b) == up;
+                v[e] = sw ? b : a;
+                v[e | jj] = sw ? a : b;
+            }
+        }
     } else {
-        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
-        if (cur != prev) {
-            if (prev != kInvalidTile) ranges[prev].y = i;
-            if (valid) ranges[cur].x = i;
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const bool up = ((base + e * 32 + lane) & k) == 0;
+            const uint64_t o = __shfl_xor_sync(0xffffffffu, v[e], j);
+            v[e] = ((v[e] < o) == (lower == up)) ? v[e] : o;
         }
     }
-    if (i == R - 1 && valid) ranges[cur].y = R;
+}
+
+// sorts src[0,n) and hands element i of the sorted sequence to emit(i, value).  s: np * 8 bytes of shared memory.
+template <int E, int THREADS, typename Emit>
+__device__ __forceinline__ void bitonic_sort_tile(const uint64_t* src, int n, int np, uint64_t* __restrict__ s, int tid,
+                                                  Emit emit) {
+    constexpr int SPAN = 32 * E;
+    const int lane = tid & 31, base = (tid >> 5) * SPAN;
+    const bool act = base < np;  // warp-uniform
+    uint64_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = base + e * 32 + lane;
+        v[e] = (act && i < n) ? src[i] : ~0ull;
+    }
+    if (act) {
+#pragma unroll
+        for (int k = 2; k <= SPAN; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) reg_stage<E>(v, j, k, base, lane);
+        }
+    }
+    const int half = np >> 1;
+    for (int k = 2 * SPAN; k <= np; k <<= 1) {
+        if (act) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) s[base + e * 32 + lane] = v[e];
+        }
+        __syncthreads();
+        for (int j = k >> 1; j >= SPAN; j >>= 1) {
+            for (int t = tid; t < half; t += THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const uint64_t a = s[i], b = s[l];
+                if ((a > b) == ((i & k) == 0)) {
+                    s[i] = b;
+                    s[l] = a;
+                }
+            }
+            __syncthreads();
+        }
+        if (act) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = s[base + e * 32 + lane];
+#pragma unroll
+            for (int j = SPAN >> 1; j > 0; j >>= 1) reg_stage<E>(v, j, k, base, lane);
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = base + e * 32 + lane;
+            if (i < n) emit(i, v[e]);
+        }
+    }
+}
+
+__device__ __forceinline__ int pow2_at_least(int n) {
+    int np = 64;
+    while (np < n) np <<= 1;
+    return np;
+}
+
+struct EmitSorted {  // final outputs: the reference's point_list_keys / point_list
+    uint64_t* keys;
+    uint32_t* point_list;
+    uint64_t tile_hi;
+    __device__ __forceinline__ void operator()(int i, uint64_t v) const {
+        keys[i] = tile_hi | (v >> 32);
+        point_list[i] = (uint32_t)v;
+    }
+};
+struct EmitRaw {  // sorted chunk back to the bucket (input of the merge passes)
+    uint64_t* dst;
+    __device__ __forceinline__ void operator()(int i, uint64_t v) const { dst[i] = v; }
+};
+
+// one CTA per tile, tiles of at most kSmallCap instances
+__global__ void __launch_bounds__(256)
+tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cursor,
+                       const uint64_t* __restrict__ bucket, uint64_t* __restrict__ keys, uint32_t* __restrict__ point_list,
+                       uint32_t* __restrict__ counters) {
+    __shared__ uint64_t s[kSmallCap];
+    const uint32_t tile = blockIdx.x;
+    const uint2 r = ranges[tile];
+    const int n = (int)(r.y - r.x), tid = threadIdx.x;
+    if (n == 0 || n > kSmallCap) return;
+    if (tid == 0 && cursor[tile] != r.y) atomicOr(counters + 2, 2u);  // histogram and emission disagree
+    const int np = pow2_at_least(n);
+    const EmitSorted emit{keys + r.x, point_list + r.x, (uint64_t)tile << 32};
+    if (np <= 512)
+        bitonic_sort_tile<2, 256>(bucket + r.x, n, np, s, tid, emit);
+    else if (np == 1024)
+        bitonic_sort_tile<4, 256>(bucket + r.x, n, np, s, tid, emit);
+    else
+        bitonic_sort_tile<8, 256>(bucket + r.x, n, np, s, tid, emit);
+}
+
+// merge of two sorted runs a[0,na) and b[0,nb) (unique keys): output element range [o0,o1) by merge path
+// (plain pointers on purpose: the runs were written by this CTA in the previous pass, no read-only cache path)
+__device__ __forceinline__ void merge_range(const uint64_t* a, int na, const uint64_t* b, int nb, uint64_t* out, int o0,
+                                            int o1) {
+    // co-rank: i = number of elements taken from a among the first o0 outputs
+    int lo = max(0, o0 - nb), hi = min(o0, na);
+    while (lo < hi) {
+        const int i = (lo + hi) >> 1;  // candidate: i from a, o0-i from b
+        if (a[i] < b[o0 - i - 1]) lo = i + 1; else hi = i;
+    }
+    int i = lo, j = o0 - lo;
+    for (int o = o0; o < o1; ++o) {
+        const bool take_a = (j >= nb) || (i < na && a[i] < b[j]);
+        out[o] = take_a ? a[i++] : b[j++];
+    }
+}
+
+// persistent CTAs over the list of long tiles: up to kLargeCap entries in shared memory, beyond that
+// chunk sort + global merge passes (bucket <-> scratch)
+__global__ void __launch_bounds__(kLargeThreads)
+tile_sort_large_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cursor,
+                       const uint32_t* __restrict__ large_tiles, uint64_t* bucket, uint64_t* scratch, uint64_t* keys,
+                       uint32_t* point_list,
+                       uint32_t* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
+    const int tid = threadIdx.x;
+    const uint32_t n_large = counters[3];
+    for (uint32_t w = blockIdx.x; w < n_large; w += gridDim.x) {
+        const uint32_t tile = large_tiles[w];
+        const uint2 r = ranges[tile];
+        const int n = (int)(r.y - r.x);
+        if (tid == 0 && cursor[tile] != r.y) atomicOr(counters + 2, 2u);
+        if (n <= kLargeCap) {
+            const int np = pow2_at_least(n);
+            const EmitSorted emit{keys + r.x, point_list + r.x, (uint64_t)tile << 32};
+            if (np <= 4096)
+                bitonic_sort_tile<4, kLargeThreads>(bucket + r.x, n, np, s, tid, emit);
+            else if (np == 8192)
+                bitonic_sort_tile<8, kLargeThreads>(bucket + r.x, n, np, s, tid, emit);
+            else
+                bitonic_sort_tile<16, kLargeThreads>(bucket + r.x, n, np, s, tid, emit);
+            __syncthreads();
+            continue;
+        }
+        // chunk sort in place
+        uint64_t* a = bucket + r.x;
+        uint64_t* b = scratch + r.x;
+        for (int c0 = 0; c0 < n; c0 += kLargeCap) {
+            const int cn = min(kLargeCap, n - c0);
+            bitonic_sort_tile<16, kLargeThreads>(a + c0, cn, kLargeCap, s, tid, EmitRaw{a + c0});
+            __syncthreads();
+        }
+        // pairwise merge passes, every thread produces a contiguous slice of each merged pair
+        for (int run = kLargeCap; run < n; run <<= 1) {
+            __threadfence_block();
+            __syncthreads();
+            for (int p0 = 0; p0 < n; p0 += 2 * run) {
+                const int na = min(run, n - p0), nb = max(0, min(run, n - p0 - run));
+                const int total = na + nb;
+                const int per = (total + kLargeThreads - 1) / kLargeThreads;
+                const int o0 = min(total, tid * per), o1 = min(total, o0 + per);
+                if (o0 < o1) merge_range(a + p0, na, a + p0 + run, nb, b + p0, o0, o1);
+            }
+            uint64_t* t = a;
+            a = b;
+            b = t;
+        }
+        __threadfence_block();
+        __syncthreads();
+        const EmitSorted emit{keys + r.x, point_list + r.x, (uint64_t)tile << 32};
+        for (int i = tid; i < n; i += kLargeThreads) emit(i, a[i]);
+        __syncthreads();
+    }
 }
 
 }  // namespace
 
 cudaError_t launch_duplicate(int P, const Frame& f, const Settings& s, const GeometryState& g, const int* radii,
-                             uint64_t* keys, uint32_t* values, cudaStream_t stream) {
+                             const ImageState& img, const BinningState& b, size_t cap, cudaStream_t stream) {
     const int blocks = (P + 255) / 256;
     const bool tbc = s.tile_based_culling;
-#define STP_DUP(TBC_, ORDER_) duplicate_kernel<TBC_, ORDER_><<<blocks, 256, 0, stream>>>(P, f, g, radii, keys, values)
+#define STP_DUP(TBC_, ORDER_) \
+    duplicate_kernel<TBC_, ORDER_><<<blocks, 256, 0, stream>>>(P, f, g, radii, img.tile_cursor, b.bucket, (uint32_t)cap)
     switch (s.sort_order) {
         case 0:
         case 1:
@@ -212,18 +431,29 @@ cudaError_t launch_duplicate(int P, const Frame& f, const Settings& s, const Geo
     return cudaGetLastError();
 }
 
-size_t sort_temp_bytes(size_t R) { return radix_sort_temp_bytes(R); }
-int sort_kernel_launches(size_t R, int end_bit) { return radix_sort_kernel_launches(R, end_bit); }
-
-cudaError_t launch_sort(BinningState& b, size_t R, int end_bit, cudaStream_t stream) {
-    return radix_sort_pairs(b.sort_space, b.sort_bytes, b.keys_unsorted, b.keys, b.point_list_unsorted, b.point_list, R,
-                            end_bit, stream);
+cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const ImageState& img, cudaStream_t stream) {
+    const int tiles = f.grid_x * f.grid_y;
+    tile_scan_kernel<<<(tiles + kScanThreads - 1) / kScanThreads, kScanThreads, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_cursor,
+                                                    img.large_tiles, g.counters);
+    return cudaGetLastError();
 }
 
-cudaError_t launch_tile_ranges(size_t R, const uint64_t* keys, uint2* ranges, int tiles, cudaStream_t stream) {
-    cudaError_t e = cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)tiles, stream);
-    if (e != cudaSuccess) return e;
-    if (R > 0) tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>((uint32_t)R, keys, ranges);
+int sort_kernel_launches() { return 2; }
+
+cudaError_t launch_tile_sort(const Frame& f, const GeometryState& g, const ImageState& img, const BinningState& b,
+                             cudaStream_t stream) {
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(tile_sort_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(kLargeCap * sizeof(uint64_t)));
+    }
+    tile_sort_small_kernel<<<f.grid_x * f.grid_y, 256, 0, stream>>>(img.ranges, img.tile_cursor, b.bucket, b.keys,
+                                                                    b.point_list, g.counters);
+    tile_sort_large_kernel<<<sm_count, kLargeThreads, kLargeCap * sizeof(uint64_t), stream>>>(
+        img.ranges, img.tile_cursor, img.large_tiles, b.bucket, b.scratch, b.keys, b.point_list, g.counters);
     return cudaGetLastError();
 }
 

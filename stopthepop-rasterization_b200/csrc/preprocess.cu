@@ -1,14 +1,13 @@
-// preprocess.cu -- per-Gaussian projection, culling, tile counting, SH->RGB and the offset scan,
-// fused in ONE kernel.
+// preprocess.cu -- per-Gaussian projection, culling, tile counting (+ the per-tile instance histogram that sizes
+// the tile buckets of binning.cu) and SH->RGB in ONE kernel.
 //
-// Replaces: preprocessCUDA<3,TBC,LB> (forward.cu:68-229) + cub::DeviceScan::InclusiveSum
-// (rasterizer_impl.cu:313) + checkFrustum (rasterizer_impl.cu:113-128).
+// Replaces: preprocessCUDA<3,TBC,LB> (forward.cu:68-229) + checkFrustum (rasterizer_impl.cu:113-128); the
+// reference's cub::DeviceScan::InclusiveSum over tiles_touched (rasterizer_impl.cu:313) has no counterpart: instance
+// slots are claimed per tile, the only prefix sum left is over the tiles (tile_scan_kernel, binning.cu).
 //
 // B200 design notes
 //   * one thread per Gaussian, 256-thread CTAs, grid sized by P (memory-bound: ~236 B in, ~90-140 B out
-//     per Gaussian); CTAs take a dynamic ticket so the single-pass decoupled-look-back scan can never
-//     dead-lock and point_offsets come out in Gaussian-index order (needed for the stable tie order of
-//     the sort: equal (tile,depth) keys stay in ascending Gaussian index, like the reference).
+//     per Gaussian); no inter-CTA dependency of any kind.
 //   * SH coefficients (192 of the 236 input bytes) are only read for survivors and are pulled
 //     warp-cooperatively: the 32 lanes stream one survivor's contiguous 12*M bytes with coalesced
 //     loads into shared memory (row stride M*3+1 -> conflict-free), instead of 48 strided scalar
@@ -119,16 +118,11 @@ __device__ __forceinline__ void stage_sh_rows(const float* __restrict__ wsrc, in
 
 template <bool TBC>
 __global__ void __launch_bounds__(kPreprocessThreads)
-preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g) {
+preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restrict__ tile_count) {
     extern __shared__ float s_sh[];  // [8 warps][32 rows][sh_stride]
-    __shared__ uint32_t s_ticket;
-    __shared__ uint32_t s_warp_sum[kPreprocessThreads / 32];
-    __shared__ uint32_t s_prefix;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_ticket = atomicAdd(&g.counters[0], 1u);
-    __syncthreads();
-    const uint32_t bid = s_ticket;
+    const uint32_t bid = blockIdx.x;
     const int idx = bid * kPreprocessThreads + tid;
     const bool valid = idx < a.P;
 
@@ -216,30 +210,52 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g) {
         }
     }
 
-    if constexpr (TBC) {
-        // exact tile count: owner thread tests the first kSeqTiles tiles, the warp shares the rest
+    {
+        // per-tile instance histogram (sizes the tile buckets of binning.cu) and, with tile_based_culling, the
+        // exact tile count: the owner thread visits the first kSeqTiles tiles, the warp shares the rest
         const int rect_tiles = alive ? (int)tiles : 0;
         const int rw = max(rc.x1 - rc.x0, 1);
         int count = 0;
-        for (int t = 0; t < min(rect_tiles, kSeqTiles); ++t)
-            count += tile_contributes(co.x, co.y, co.z, mean2D, thr, rc.x0 + t % rw, rc.y0 + t / rw) ? 1 : 0;
+        for (int t = 0, tx = rc.x0, ty = rc.y0; t < min(rect_tiles, kSeqTiles); ++t) {
+            if (!TBC || tile_contributes(co.x, co.y, co.z, mean2D, thr, tx, ty)) {
+                ++count;
+                atomicAdd(tile_count + ty * f.grid_x + tx, 1u);
+            }
+            if (++tx == rc.x1) {
+                tx = rc.x0;
+                ++ty;
+            }
+        }
         uint32_t big = __ballot_sync(0xffffffffu, rect_tiles > kSeqTiles);
         while (big) {
             const int src = __ffs(big) - 1;
             big &= big - 1;
-            const float A = __shfl_sync(0xffffffffu, co.x, src), B = __shfl_sync(0xffffffffu, co.y, src),
-                        C = __shfl_sync(0xffffffffu, co.z, src);
-            const float2 m = make_float2(__shfl_sync(0xffffffffu, mean2D.x, src), __shfl_sync(0xffffffffu, mean2D.y, src));
-            const float th = __shfl_sync(0xffffffffu, thr, src);
+            float A = 0.f, B = 0.f, C = 0.f, th = 0.f;
+            float2 m = make_float2(0.f, 0.f);
+            if constexpr (TBC) {
+                A = __shfl_sync(0xffffffffu, co.x, src);
+                B = __shfl_sync(0xffffffffu, co.y, src);
+                C = __shfl_sync(0xffffffffu, co.z, src);
+                m = make_float2(__shfl_sync(0xffffffffu, mean2D.x, src), __shfl_sync(0xffffffffu, mean2D.y, src));
+                th = __shfl_sync(0xffffffffu, thr, src);
+            }
             const int x0 = __shfl_sync(0xffffffffu, rc.x0, src), y0 = __shfl_sync(0xffffffffu, rc.y0, src);
             const int w = __shfl_sync(0xffffffffu, rw, src), n = __shfl_sync(0xffffffffu, rect_tiles, src);
             int c = 0;
-            for (int t = kSeqTiles + lane; t < n; t += 32) c += tile_contributes(A, B, C, m, th, x0 + t % w, y0 + t / w) ? 1 : 0;
+            for (int t = kSeqTiles + lane; t < n; t += 32) {
+                const int tx = x0 + t % w, ty = y0 + t / w;
+                if (!TBC || tile_contributes(A, B, C, m, th, tx, ty)) {
+                    ++c;
+                    atomicAdd(tile_count + ty * f.grid_x + tx, 1u);
+                }
+            }
+            if constexpr (TBC) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (lane == src) count += c;
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                if (lane == src) count += c;
+            }
         }
-        if (alive) {
+        if (TBC && alive) {
             tiles = (uint32_t)count;
             if (tiles == 0) alive = false;
         }
@@ -310,57 +326,6 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g) {
         g.tiles_touched[idx] = tiles;
     }
 
-    // ---- inclusive scan of tiles over the whole grid (decoupled look-back) --------------------
-    uint32_t incl = tiles;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp_sum[warp] = incl;
-    __syncthreads();
-    uint32_t warp_off = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < kPreprocessThreads / 32; ++w) {
-        const uint32_t v = s_warp_sum[w];
-        if (w < warp) warp_off += v;
-        block_total += v;
-    }
-    if (warp == 0) {
-        constexpr unsigned long long FLAG_AGG = 1ull << 32, FLAG_INC = 2ull << 32;
-        volatile unsigned long long* st = g.scan_state;
-        uint32_t excl = 0;
-        if (bid == 0) {
-            if (lane == 0) st[0] = FLAG_INC | block_total;
-        } else {
-            if (lane == 0) st[bid] = FLAG_AGG | block_total;
-            int look = (int)bid - 1;
-            while (true) {
-                const int j = look - lane;
-                unsigned long long v = (j >= 0) ? st[j] : FLAG_INC;
-                while (__any_sync(0xffffffffu, (v >> 32) == 0)) v = (j >= 0) ? st[j] : FLAG_INC;
-                const uint32_t inc_mask = __ballot_sync(0xffffffffu, (v >> 32) == 2);
-                // lanes before (and including) the first inclusive flag contribute
-                const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
-                uint32_t c = (lane <= first_inc) ? (uint32_t)(v & 0xffffffffull) : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                excl += c;
-                if (inc_mask) break;
-                look -= 32;
-            }
-            if (lane == 0) {
-                __threadfence();
-                st[bid] = FLAG_INC | (unsigned long long)(excl + block_total);
-            }
-        }
-        if (lane == 0) {
-            s_prefix = excl;
-            if (bid == gridDim.x - 1) g.counters[1] = excl + block_total;  // R
-        }
-    }
-    __syncthreads();
-    if (valid) g.point_offsets[idx] = s_prefix + warp_off + incl;
 }
 
 // markVisible (rasterizer_impl.cu:113-128): the same near-plane test, nothing else.
@@ -372,20 +337,20 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
     present[idx] = !(pv.z <= kNearPlane);
 }
 
-cudaError_t launch_preprocess(const PreprocessArgs& a, const Frame& f, const GeometryState& g, bool tbc,
-                              cudaStream_t stream) {
+cudaError_t launch_preprocess(const PreprocessArgs& a, const Frame& f, const GeometryState& g, uint32_t* tile_count,
+                              bool tbc, cudaStream_t stream) {
     const int blocks = (a.P + kPreprocessThreads - 1) / kPreprocessThreads;
-    cudaError_t e = cudaMemsetAsync(g.scan_state, 0, sizeof(unsigned long long) * blocks, stream);
+    cudaError_t e = cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * 64, stream);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * 64, stream);
+    e = cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * (size_t)f.grid_x * f.grid_y, stream);
     if (e != cudaSuccess) return e;
     const size_t smem = (a.colors_precomp == nullptr && a.M > 0) ? sizeof(float) * 8 * 32 * (a.M * 3 + 1) : 0;
     if (tbc) {
         cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        preprocess_kernel<true><<<blocks, kPreprocessThreads, smem, stream>>>(a, f, g);
+        preprocess_kernel<true><<<blocks, kPreprocessThreads, smem, stream>>>(a, f, g, tile_count);
     } else {
         cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        preprocess_kernel<false><<<blocks, kPreprocessThreads, smem, stream>>>(a, f, g);
+        preprocess_kernel<false><<<blocks, kPreprocessThreads, smem, stream>>>(a, f, g, tile_count);
     }
     return cudaGetLastError();
 }

@@ -4,7 +4,7 @@
 // with its device functions computeColorFromSH backward (backward.cu:22-141) and computeCov3D
 // backward (backward.cu:316-379).  The reference runs two kernels that both re-read the mean, radii
 // and (through global memory) dL_dcov3D / dL_dmean3D; here one thread keeps them in registers.
-// Gaussians with radii<=0 are skipped: their gradient rows stay at the caller's zeros.
+// Gaussians with radii<=0 get zero rows written here (the caller does not pre-clear the outputs).
 // Gradients are not integer-decision inputs, so this file uses ordinary float expressions
 // (tolerance 1e-5 relative vs. the reference).
 #include "stp_kernels.cuh"
@@ -80,25 +80,60 @@ preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
     extern __shared__ float s_rows[];  // [8 warps][32 rows][3M+1]
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool alive = idx < a.P && a.radii[idx] > 0;
+    const bool valid = idx < a.P;
+    const bool alive = valid && a.radii[idx] > 0;
     const uint32_t live = __ballot_sync(0xffffffffu, alive);
-    if (live == 0) return;
     const int n_sh = a.M * 3, sh_stride = n_sh + 1;
-    float* const my_rows = s_rows + (size_t)warp * 32 * sh_stride;
     const int warp_base = blockIdx.x * blockDim.x + warp * 32;
-    const bool sh_staged = a.shs != nullptr && n_sh > 0 &&
-                           ((reinterpret_cast<uintptr_t>(a.shs + (size_t)warp_base * n_sh) |
-                             reinterpret_cast<uintptr_t>(a.dL_dsh + (size_t)warp_base * n_sh)) & 15u) == 0;
+    const int rows = min(32, a.P - warp_base);
+    const bool has_sh = a.shs != nullptr && n_sh > 0;
+    // Every row of dL_dmean3D / dL_dcov3D / dL_dscale / dL_drot / dL_dsh is written here: culled Gaussians get
+    // zeros, so the caller does not have to clear these buffers (the reference memsets 256 B per Gaussian per
+    // iteration for them, rasterize_points.cu:178-186).
+    if (valid && !alive) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.dL_dmean3D[3 * idx + k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * idx + k] = 0.f;
+        if (a.scales != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a.dL_dscale[3 * idx + k] = 0.f;
+            reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const bool rows_aligned = has_sh && ((reinterpret_cast<uintptr_t>(a.shs + (size_t)warp_base * n_sh) |
+                                          reinterpret_cast<uintptr_t>(a.dL_dsh + (size_t)warp_base * n_sh)) & 15u) == 0;
+    if (live == 0) {
+        if (has_sh && rows > 0) {  // whole warp culled: clear its 32 gradient rows with coalesced stores
+            float* dst = a.dL_dsh + (size_t)warp_base * n_sh;
+            const int total = rows * n_sh;
+            if (rows_aligned && (total & 3) == 0) {
+                for (int i = lane; 4 * i < total; i += 32) reinterpret_cast<float4*>(dst)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int i = lane; i < total; i += 32) dst[i] = 0.f;
+            }
+        }
+        return;
+    }
+    float* const my_rows = s_rows + (size_t)warp * 32 * sh_stride;
+    const bool sh_staged = rows_aligned;
     if (sh_staged) {
-        move_sh_rows<false>(const_cast<float*>(a.shs) + (size_t)warp_base * n_sh, min(32, a.P - warp_base), n_sh, live, lane,
-                            my_rows, sh_stride);
+        move_sh_rows<false>(const_cast<float*>(a.shs) + (size_t)warp_base * n_sh, rows, n_sh, live, lane, my_rows, sh_stride);
         __syncwarp();
     }
-    if (alive) preprocess_bwd_one(a, f, idx, sh_staged ? my_rows + lane * sh_stride : nullptr);
+    if (alive) {
+        preprocess_bwd_one(a, f, idx, sh_staged ? my_rows + lane * sh_stride : nullptr);
+    } else if (valid && has_sh) {
+        if (sh_staged) {
+            for (int k = 0; k < n_sh; ++k) my_rows[lane * sh_stride + k] = 0.f;
+        } else {
+            for (int k = 0; k < n_sh; ++k) a.dL_dsh[(size_t)idx * n_sh + k] = 0.f;
+        }
+    }
     if (sh_staged) {
         __syncwarp();
-        move_sh_rows<true>(a.dL_dsh + (size_t)warp_base * n_sh, min(32, a.P - warp_base), n_sh, live, lane, my_rows,
-                           sh_stride);
+        const uint32_t all_rows = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
+        move_sh_rows<true>(a.dL_dsh + (size_t)warp_base * n_sh, rows, n_sh, all_rows, lane, my_rows, sh_stride);
     }
 }
 

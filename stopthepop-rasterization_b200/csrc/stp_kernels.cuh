@@ -72,17 +72,17 @@ struct PreprocessBwdArgs {
     float* dL_drot;
 };
 
-cudaError_t launch_preprocess(const PreprocessArgs& a, const Frame& f, const GeometryState& g, bool tbc,
-                              cudaStream_t stream);
+cudaError_t launch_preprocess(const PreprocessArgs& a, const Frame& f, const GeometryState& g, uint32_t* tile_count,
+                              bool tbc, cudaStream_t stream);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t stream);
 
 // binning.cu
-size_t sort_temp_bytes(size_t R);
-int sort_kernel_launches(size_t R, int end_bit);  // own kernels per sort (0 while the sort is a library call)
+int sort_kernel_launches();  // own kernels per tile sort
+cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const ImageState& img, cudaStream_t stream);
 cudaError_t launch_duplicate(int P, const Frame& f, const Settings& s, const GeometryState& g, const int* radii,
-                             uint64_t* keys, uint32_t* values, cudaStream_t stream);
-cudaError_t launch_sort(BinningState& b, size_t R, int end_bit, cudaStream_t stream);
-cudaError_t launch_tile_ranges(size_t R, const uint64_t* keys, uint2* ranges, int tiles, cudaStream_t stream);
+                             const ImageState& img, const BinningState& b, size_t cap, cudaStream_t stream);
+cudaError_t launch_tile_sort(const Frame& f, const GeometryState& g, const ImageState& img, const BinningState& b,
+                             cudaStream_t stream);
 
 // render_global.cu
 cudaError_t launch_render_global_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream);

@@ -22,8 +22,8 @@ static inline void obtain(char*& chunk, T*& ptr, size_t count) {
     chunk = reinterpret_cast<char*>(ptr + count);
 }
 
-// per-Gaussian scratch: 87 B (+48 B with inverse covariance) like the reference, plus the
-// decoupled-look-back scan state (8 B per 256 Gaussians) that replaces the CUB scan temp.
+// per-Gaussian scratch: 83 B (+48 B with inverse covariance).  The reference's point_offsets / scan temp do not
+// exist here: instance slots are claimed per tile (binning.cu), not per Gaussian.
 struct GeometryState {
     float* depths;
     uint8_t* clamped;
@@ -34,9 +34,7 @@ struct GeometryState {
     float4* conic_opacity;
     float* rgb;
     uint32_t* tiles_touched;
-    uint32_t* point_offsets;
-    unsigned long long* scan_state;  // [ceil(P/256)] (flag<<32 | value)
-    uint32_t* counters;              // [0] dynamic CTA ticket, [1] R (total instances), [2] error flags
+    uint32_t* counters;  // [1] R (total instances), [2] error flags, [3] number of tiles on the large-tile sort list
 
     static GeometryState from_chunk(char*& chunk, size_t P, bool inv) {
         GeometryState g;
@@ -50,8 +48,6 @@ struct GeometryState {
         obtain(chunk, g.conic_opacity, P);
         obtain(chunk, g.rgb, P * 3);
         obtain(chunk, g.tiles_touched, P);
-        obtain(chunk, g.point_offsets, P);
-        obtain(chunk, g.scan_state, (P + kPreprocessThreads - 1) / kPreprocessThreads);
         obtain(chunk, g.counters, 64);
         return g;
     }
@@ -61,30 +57,38 @@ struct ImageState {
     float* final_T;
     uint32_t* n_contrib;
     uint2* ranges;
+    // tile-bucket binning (binning.cu): per-tile instance histogram filled by preprocess, the running
+    // slot cursor of every tile's bucket, and the list of tiles too long for the small in-smem sorter
+    uint32_t* tile_count;
+    uint32_t* tile_cursor;
+    uint32_t* large_tiles;
     static ImageState from_chunk(char*& chunk, size_t N, size_t tiles) {
         ImageState s;
         obtain(chunk, s.final_T, N);
         obtain(chunk, s.n_contrib, N);
         obtain(chunk, s.ranges, tiles);
+        obtain(chunk, s.tile_count, tiles);
+        obtain(chunk, s.tile_cursor, tiles);
+        obtain(chunk, s.large_tiles, tiles);
         return s;
     }
 };
 
+// per-instance arena: 28 B/instance.  point_list / keys are the sorted outputs (the reference's
+// point_list / point_list_keys, rasterizer_impl.h:57-67); bucket holds the unsorted
+// (depth bits << 32 | Gaussian index) records grouped by tile, scratch is the ping-pong buffer of the
+// global merge passes that only tiles longer than the in-smem capacity need.
 struct BinningState {
     uint32_t* point_list;
-    uint32_t* point_list_unsorted;
     uint64_t* keys;
-    uint64_t* keys_unsorted;
-    char* sort_space;
-    size_t sort_bytes;
-    static BinningState from_chunk(char*& chunk, size_t R, size_t sort_bytes) {
+    uint64_t* bucket;
+    uint64_t* scratch;
+    static BinningState from_chunk(char*& chunk, size_t R) {
         BinningState b;
         obtain(chunk, b.point_list, R);
-        obtain(chunk, b.point_list_unsorted, R);
         obtain(chunk, b.keys, R);
-        obtain(chunk, b.keys_unsorted, R);
-        obtain(chunk, b.sort_space, sort_bytes);
-        b.sort_bytes = sort_bytes;
+        obtain(chunk, b.bucket, R);
+        obtain(chunk, b.scratch, R);
         return b;
     }
 };

@@ -43,8 +43,7 @@ class StpTileBand(ctypes.Structure):
 
 class StpGeometryView(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
-        "depths", "clamped", "rects2D", "means2D", "cov3D", "cov3D_inv", "conic_opacity", "rgb", "tiles_touched",
-        "point_offsets")]
+        "depths", "clamped", "rects2D", "means2D", "cov3D", "cov3D_inv", "conic_opacity", "rgb", "tiles_touched")]
 
 
 class StpBinningView(ctypes.Structure):
@@ -198,16 +197,19 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)  # rasterize_points.cu:169-170
     M = sh.size(1) if sh is not None and sh.numel() != 0 else 0
     st = settings_from_dict(settings_dict)
-    # one zero-filled slab instead of nine torch::zeros (rasterize_points.cu:178-186).  The five PARAMETER
-    # gradients come first and contiguous, so a data-parallel caller can all-reduce them as one buffer
-    # (parallel.py); the per-view intermediates (means2D, colors, conic, cov3D) follow.
-    widths = [3, 3 * M, 1, 3, 4, 3, 3, 4, 6]  # means3D sh opacity scales rot | means2D colors conic cov3D
-    flat = torch.zeros((sum(widths) * P,), dtype=torch.float32, device=device)
+    # ONE slab instead of nine torch::zeros (rasterize_points.cu:178-186).  Only the four atomically accumulated
+    # arrays (opacity, means2D, colors, conic: 44 B/Gaussian) are cleared; every row of the other five is written by
+    # the preprocess-backward kernel (zeros for culled Gaussians), so 256 B/Gaussian of memset disappear.  The five
+    # PARAMETER gradients come first and contiguous, so a data-parallel caller can all-reduce them as one buffer
+    # (stp_sharding.py); the per-view intermediates (means2D, colors, conic, cov3D) follow.
+    widths = [3, 3 * M, 3, 4, 1, 3, 3, 4, 6]  # means3D sh scales rot opacity | means2D colors conic | cov3D
+    flat = torch.empty((sum(widths) * P,), dtype=torch.float32, device=device)
+    flat[sum(widths[:4]) * P:sum(widths[:8]) * P].zero_()
     views, off = [], 0
     for w in widths:
         views.append(flat[off:off + w * P])
         off += w * P
-    dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drot, dL_dmeans2D, dL_dcolors, dL_dconic, dL_dcov3D = views
+    dL_dmeans3D, dL_dsh, dL_dscales, dL_drot, dL_dopacity, dL_dmeans2D, dL_dcolors, dL_dconic, dL_dcov3D = views
     param_slab = flat[:sum(widths[:5]) * P]
     if P != 0:
         means3D = _f32(means3D, device)
@@ -270,8 +272,7 @@ def view_geometry(geomBuffer, P, settings_dict):
                 cov3D_inv=(_wrap(v.cov3D_inv, geomBuffer, 12 * P, f32).view(P, 3, 4) if v.cov3D_inv else None),
                 conic_opacity=_wrap(v.conic_opacity, geomBuffer, 4 * P, f32).view(P, 4),
                 rgb=_wrap(v.rgb, geomBuffer, 3 * P, f32).view(P, 3),
-                tiles_touched=_wrap(v.tiles_touched, geomBuffer, P, u32),
-                point_offsets=_wrap(v.point_offsets, geomBuffer, P, u32))
+                tiles_touched=_wrap(v.tiles_touched, geomBuffer, P, u32))
 
 
 def view_binning(binningBuffer, R):

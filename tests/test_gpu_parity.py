@@ -223,6 +223,49 @@ def test_full_size_properties_and_reference(cfg, mode):
         assert (a - b).abs().max().item() <= max(TOL, 10 * noise) * m
 
 
+@pytest.mark.parametrize("P,order,min_len", [(15_000, 0, 1000), (60_000, 0, 2048), (250_000, 0, 16384),
+                                             (250_000, 3, 16384)])
+def test_long_tile_lists_sort_paths(P, order, min_len):
+    """tile-bucket sorter (binning.cu): tiles of ~1.5k (one small CTA), ~6k (one 128 KB CTA) and ~25k instances
+    (chunk sort + global merge passes) on a 64x48 image.  point_list must be the stable (tile, depth bits) order:
+    checked as a property (keys ascending, equal keys in ascending Gaussian index, ranges partition the list) and
+    bit-exactly against the reference build when oracle/_ref is present."""
+    from diff_gaussian_rasterization import _C
+    from oracle import ref_api as ref
+    import stp_scenes as S
+    dev = _dev()
+    sc, cam = S.make_scene(P, 64, 48, 77 + P, sigma_scale=0.25)
+    # the second half of the cloud repeats the positions of the first: pairs of equal keys exercise the tie order
+    sc.means3D[P // 2:] = sc.means3D[:P - P // 2]
+    sc, cam = S.to_device(sc, dev), S.to_device(cam, dev)
+    d = S.default_settings_dict(sort_order=order, tile_based_culling=(order == 3))
+    e = torch.empty(0, device=dev)
+    out = _C.rasterize_gaussians(cam.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e, cam.viewmatrix,
+                                 cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx, cam.tanfovy, 48, 64, sc.shs, 3,
+                                 cam.campos, False, d, False, False)
+    R, color, radii, geom, binning, img = out
+    b = _C.view_binning(binning, R)
+    keys, pl = b["point_list_keys"], b["point_list"].long()
+    ranges = _C.view_image(img, 64, 48)["ranges"].long()
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert int(lens.sum()) == R and int(lens.max()) > min_len, int(lens.max())
+    assert int(same_keys := (keys[1:] == keys[:-1]).sum()) > 0 or order != 0
+    assert bool((keys[1:] >= keys[:-1]).all())
+    same = keys[1:] == keys[:-1]
+    assert bool((pl[1:][same] > pl[:-1][same]).all())
+    assert bool(((keys >> 32)[ranges[lens > 0, 0]] == torch.nonzero(lens > 0).squeeze(1)).all())
+    if order == 0:
+        depths = _C.view_geometry(geom, P, d)["depths"]
+        assert torch.equal((keys & 0xFFFFFFFF).int(), depths[pl].view(torch.int32))
+    if not ref.available():
+        pytest.skip("oracle/_ref not shipped: reference-build comparison skipped (properties checked)")
+    rr = ref.forward(sc, cam, d)
+    assert rr[0] == R
+    assert torch.equal(ref.decode_binning(rr[4], R)["point_list"], b["point_list"])
+    assert torch.equal(ref.decode_image(rr[5], 64, 48)["ranges"], ranges.int())
+    assert (rr[1] - color).abs().max().item() <= TOL * rr[1].abs().max().item()
+
+
 def test_tile_band_sharding_reproduces_single_gpu_buffers(golden):
     """concatenating the per-band point lists / images of a tile-row sharding equals the
     single-GPU result bit for bit, and the summed band gradients equal the full gradients."""
