@@ -30,8 +30,20 @@
 #ifndef STP_HIER_MIDBATCH
 #define STP_HIER_MIDBATCH 0
 #endif
-#ifndef STP_HIER_MINB
-#define STP_HIER_MINB 3
+#ifndef STP_HIER_MINB_FWD  // resident CTAs per SM asked from ptxas (register cap 48 / 64): the kernels are latency bound and
+#define STP_HIER_MINB_FWD 5  // occupancy limited by registers; A/B on B200: fwd 3->5 CTAs -22 %, bwd 3->4 CTAs -10 % (5: worse, spills)
+#endif
+#ifndef STP_HIER_MINB_BWD
+#define STP_HIER_MINB_BWD 4
+#endif
+#ifndef STP_HIER_FIFO      // defer mid/head work through the per-block FIFO until both blocks of a warp have a group
+#define STP_HIER_FIFO 0
+#endif
+#ifndef STP_HIER_COMPACT   // with 4x4 culling: compact the surviving entries of a batch before ranking them
+#define STP_HIER_COMPACT 1
+#endif
+#ifndef STP_HIER_PREFILTER // with 4x4 culling: bounding-box rejection before the exact contribution test
+#define STP_HIER_PREFILTER 0
 #endif
 
 namespace stp {
@@ -42,6 +54,9 @@ constexpr float kFltMax = 3.402823466e+38f;
 constexpr int kDeadBit = 0x40000000;  // entry cannot reach any pixel of the 4x4 block (ids are < 2^30)
 constexpr int kIdMask = 0x3fffffff;
 constexpr int kTailStride = 80;  // 64 entries + 16 pad: the two blocks of a warp live in disjoint banks
+constexpr int kFifoGroups = 16;  // capacity of the tail -> mid hand-over queue of a block, in groups of 4 ids
+constexpr int kFifoIds = kFifoGroups * 4;
+constexpr int kFifoLimit = 8;    // backlog a block may keep while the other block of its warp has nothing to do
 
 template <int MID>
 struct HierShared {
@@ -54,8 +69,16 @@ struct HierShared {
     float mid_d[64 * kMidStride];
     int mid_id[64 * kMidStride];
     int out_id[64 * 4];
+    int fifo_id[16 * kFifoIds];  // popped tail groups waiting for the mid stage, per block
     float tail_ray[16 * 3];
     float mid_ray[64 * 3];
+    float pix_ray[3 * 256];  // per-pixel view ray, [component][thread]: only read by the few entries that pass the alpha test
+};
+// backward only: per-pixel constants of the gradient formulas, [k][thread] (k: g0 g1 g2 f0 f1 f2 T_final bg_dot).  Kept in
+// shared memory instead of eight registers per thread: they are only touched when a pixel actually blends an entry,
+// and the kernel is occupancy-limited by registers.
+struct HierSharedBwd {
+    float pix_const[8 * 256];
 };
 
 struct GaussRec {
@@ -95,15 +118,15 @@ struct PixelState<false> {
 template <>
 struct PixelState<true> {
     float T, C0, C1, C2;
-    float T_final, g0, g1, g2, f0, f1, f2;
 };
 
 template <int HEAD, int MID, bool CULL, bool BWD>
-__global__ void __launch_bounds__(256, (HEAD <= 4 && MID <= 12) ? STP_HIER_MINB : 1)
+__global__ void __launch_bounds__(256, (HEAD <= 4 && MID <= 12) ? (BWD ? STP_HIER_MINB_BWD : STP_HIER_MINB_FWD) : 1)
 render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Sh = HierShared<MID>;
     Sh& sh = *reinterpret_cast<Sh*>(smem_raw);
+    float* const pc = reinterpret_cast<HierSharedBwd*>(smem_raw + sizeof(Sh))->pix_const + threadIdx.x;  // BWD only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, hl = lane & 15;
@@ -128,7 +151,10 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     const float* __restrict__ colors = BWD ? ab.colors : a.colors;
 
     const RayCam cam = make_raycam(f.inv_viewproj, f.cam_pos, f.W, f.H);
-    const Vec3 ray = view_ray(cam, pxf, pyf);  // the pixel's own ray (no half-pixel offset, :355)
+    {
+        const Vec3 r = view_ray(cam, pxf, pyf);  // the pixel's own ray (no half-pixel offset, :355)
+        sh.pix_ray[tid] = r.x; sh.pix_ray[256 + tid] = r.y; sh.pix_ray[512 + tid] = r.z;
+    }
     if (hl == 0) {
         const Vec3 r = view_ray(cam, fadd((float)cx, 1.5f), fadd((float)cy, 1.5f));
         sh.tail_ray[b * 3 + 0] = r.x; sh.tail_ray[b * 3 + 1] = r.y; sh.tail_ray[b * 3 + 2] = r.z;
@@ -142,19 +168,21 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     PixelState<BWD> ps;
     ps.T = 1.0f;
     ps.C0 = ps.C1 = ps.C2 = 0.f;
-    float bg_dot = 0.f;
     if constexpr (BWD) {
-        ps.T_final = inside ? ab.final_T[pix_id] : 0.f;
-        ps.g0 = ps.g1 = ps.g2 = ps.f0 = ps.f1 = ps.f2 = 0.f;
+        float T_final = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f;
         if (inside) {
-            ps.g0 = ab.dL_dpix[pix_id];
-            ps.g1 = ab.dL_dpix[plane + pix_id];
-            ps.g2 = ab.dL_dpix[2 * plane + pix_id];
-            ps.f0 = ab.pixel_colors[pix_id] - ps.T_final * f.background[0];
-            ps.f1 = ab.pixel_colors[plane + pix_id] - ps.T_final * f.background[1];
-            ps.f2 = ab.pixel_colors[2 * plane + pix_id] - ps.T_final * f.background[2];
+            T_final = ab.final_T[pix_id];
+            g0 = ab.dL_dpix[pix_id];
+            g1 = ab.dL_dpix[plane + pix_id];
+            g2 = ab.dL_dpix[2 * plane + pix_id];
+            f0 = ab.pixel_colors[pix_id] - T_final * f.background[0];
+            f1 = ab.pixel_colors[plane + pix_id] - T_final * f.background[1];
+            f2 = ab.pixel_colors[2 * plane + pix_id] - T_final * f.background[2];
         }
-        bg_dot = f.background[0] * ps.g0 + f.background[1] * ps.g1 + f.background[2] * ps.g2;
+        pc[0] = g0; pc[256] = g1; pc[512] = g2;
+        pc[768] = f0; pc[1024] = f1; pc[1280] = f2;
+        pc[1536] = T_final;
+        pc[1792] = f.background[0] * g0 + f.background[1] * g1 + f.background[2] * g2;
     }
     const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
     bool active = inside;
@@ -203,17 +231,18 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             ps.C1 += c1 * alpha * ps.T;
             ps.C2 += c2 * alpha * ps.T;
             const float inv_T = 1.0f / test_T;
-            float dL_dalpha = (c0 - (ps.f0 - ps.C0) * inv_T) * ps.g0 + (c1 - (ps.f1 - ps.C1) * inv_T) * ps.g1 +
-                              (c2 - (ps.f2 - ps.C2) * inv_T) * ps.g2;
+            const float g0 = pc[0], g1 = pc[256], g2 = pc[512];
+            float dL_dalpha = (c0 - (pc[768] - ps.C0) * inv_T) * g0 + (c1 - (pc[1024] - ps.C1) * inv_T) * g1 +
+                              (c2 - (pc[1280] - ps.C2) * inv_T) * g2;
             dL_dalpha *= ps.T;
-            dL_dalpha += (-ps.T_final / (1.f - alpha)) * bg_dot;
+            dL_dalpha += (-pc[1536] / (1.f - alpha)) * pc[1792];
             const float dL_dG = co.w * dL_dalpha;
             const float gdx = G * dx, gdy = G * dy;
             const float dG_ddelx = -gdx * co.x - gdy * co.y;
             const float dG_ddely = -gdy * co.z - gdx * co.y;
-            atomicAdd(ab.dL_dcolor + 3 * id + 0, dchannel_dcolor * ps.g0);
-            atomicAdd(ab.dL_dcolor + 3 * id + 1, dchannel_dcolor * ps.g1);
-            atomicAdd(ab.dL_dcolor + 3 * id + 2, dchannel_dcolor * ps.g2);
+            atomicAdd(ab.dL_dcolor + 3 * id + 0, dchannel_dcolor * g0);
+            atomicAdd(ab.dL_dcolor + 3 * id + 1, dchannel_dcolor * g1);
+            atomicAdd(ab.dL_dcolor + 3 * id + 2, dchannel_dcolor * g2);
             atomicAdd(ab.dL_dmean2D + 3 * id + 0, dL_dG * dG_ddelx * ddelx_dx);
             atomicAdd(ab.dL_dmean2D + 3 * id + 1, dL_dG * dG_ddely * ddely_dy);
             atomicAdd(ab.dL_dconic + 4 * id + 0, -0.5f * gdx * dx * dL_dG);
@@ -250,6 +279,7 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         if (alpha < kAlphaThreshold) return false;
         float ic[6], ux, uy, uz;
         load_inv(cov3D_inv, id, ic, ux, uy, uz);
+        const Vec3 ray{sh.pix_ray[tid], sh.pix_ray[256 + tid], sh.pix_ray[512 + tid]};
         ed = depth_along_ray(ic, ux, uy, uz, ray);
         es = BWD ? G : alpha;
         return !(ed < 0.0f);
@@ -275,7 +305,6 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     int* const mi = sh.mid_id + qg * Sh::kMidStride;
     int* const oi = sh.out_id + qg * 4;
     int mcount = 0, mbase = 0;  // resident entries live at md[mbase .. mbase+mcount)
-    const float mrx = sh.mid_ray[qg * 3], mry = sh.mid_ray[qg * 3 + 1], mrz = sh.mid_ray[qg * 3 + 2];
 
     // the 4 smallest mid entries (already in oi[0..3]) go to the 4 pixels of the quad
     auto quad_to_head = [&]() {
@@ -322,7 +351,7 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         if (my_id >= 0) {
             float ic[6], ux, uy, uz;
             load_inv(cov3D_inv, my_id & kIdMask, ic, ux, uy, uz);
-            const Vec3 mr{mrx, mry, mrz};
+            const Vec3 mr{sh.mid_ray[qg * 3], sh.mid_ray[qg * 3 + 1], sh.mid_ray[qg * 3 + 2]};
             my_d = depth_along_ray(ic, ux, uy, uz, mr);
         }
         return my_d;
@@ -383,7 +412,27 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     float* const nwd = sh.new_d + b * 48;
     int* const nwi = sh.new_id + b * 48;
     int tcount = 0, tbase = 0;  // resident entries live at td[tbase .. tbase+tcount)
-    const Vec3 tray{sh.tail_ray[b * 3], sh.tail_ray[b * 3 + 1], sh.tail_ray[b * 3 + 2]};
+
+    // tail -> mid hand-over queue of this block (ids only, groups of 4); fhead / fcount are identical in the 16 lanes
+    int* const ff = sh.fifo_id + b * kFifoIds;
+    int fhead = 0, fcount = 0;
+    // process queued groups while both blocks of the warp have one (convergent), or while a backlog exceeds `limit`
+    auto consume = [&](int limit) {
+        while (true) {
+            if (!__any_sync(hmask, active)) fcount = 0;  // nothing downstream of this block is listening any more
+            const uint32_t hv = __ballot_sync(0xffffffffu, fcount > 0);
+            if (hv == 0) break;
+            const bool both = (hv & 0xffffu) != 0 && (hv >> 16) != 0;
+            if (!both && !__any_sync(0xffffffffu, fcount > limit)) break;
+            if (fcount > 0) {
+                const int id_g = ff[(fhead * 4 + p) & (kFifoIds - 1)];
+                mid_push_group(id_g, mid_depth(id_g));
+                fhead = (fhead + 1) & (kFifoGroups - 1);
+                --fcount;
+            }
+            __syncwarp();
+        }
+    };
 
     const uint2 range = ranges[tile_y * f.grid_x + tile_x];
     for (uint32_t progress = range.x; progress < range.y; progress += 32) {
@@ -399,33 +448,52 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             float d = kFltMax;
             if (src < range.y) id = (int)__ldg(point_list + src);
             if (id >= 0) {
+                const float2 xy = __ldg(means2D + id);
+                const float4 co = __ldg(conic_opacity + id);
+                // conservative "cannot reach this block" test (bounding box of the alpha >= 1/255 ellipse, inflated far
+                // beyond the rounding error of the exact evaluations below and per pixel)
+                bool unreachable = false;
+                if constexpr (!CULL || STP_HIER_PREFILTER) unreachable = block_unreachable(xy, co, (float)cx, (float)cy);
                 bool culled = false;
-                if constexpr (CULL) {  // :723-743
-                    const float2 xy = __ldg(means2D + id);
-                    const float4 co = __ldg(conic_opacity + id);
-                    float mx, my;
-                    const float pw = max_contrib_power<3, 3>(co.x, co.y, co.z, xy.x, xy.y, (float)cx, (float)cy,
-                                                             fadd((float)cx, 3.0f), fadd((float)cy, 3.0f), mx, my);
-                    culled = fminf(0.99f, fmul(co.w, expf(-pw))) < kAlphaThreshold;
+                if constexpr (CULL) {  // :723-743; an unreachable entry is always rejected by the exact test as well
+                    culled = unreachable;
+                    if (!culled) {
+                        float mx, my;
+                        const float pw = max_contrib_power<3, 3>(co.x, co.y, co.z, xy.x, xy.y, (float)cx, (float)cy,
+                                                                 fadd((float)cx, 3.0f), fadd((float)cy, 3.0f), mx, my);
+                        culled = fminf(0.99f, fmul(co.w, expf(-pw))) < kAlphaThreshold;
+                    }
                 }
                 if (!culled) {
                     float ic[6], ux, uy, uz;
                     load_inv(cov3D_inv, id, ic, ux, uy, uz);
+                    const Vec3 tray{sh.tail_ray[b * 3], sh.tail_ray[b * 3 + 1], sh.tail_ray[b * 3 + 2]};
                     d = depth_along_ray(ic, ux, uy, uz, tray);
-                    if constexpr (!CULL) {
-                        // conservative "cannot reach this block" flag (bounding box of the alpha >= 1/255 ellipse,
-                        // inflated far beyond the rounding error of the per-pixel evaluation)
-                        if (block_unreachable(__ldg(means2D + id), __ldg(conic_opacity + id), (float)cx, (float)cy))
-                            id |= kDeadBit;
-                    }
+                    if (!CULL && unreachable) id |= kDeadBit;
                 } else {
                     id = -1;
                 }
             }
             e_d[s] = d;
             e_id[s] = (d == kFltMax) ? -1 : id;
-            nwd[hl + 16 * s] = e_d[s];
-            nwi[hl + 16 * s] = e_id[s];
+        }
+        // with 4x4 culling only a few of the 32 entries survive: compact them (list order kept) into new_d/new_id so
+        // that every later step costs O(valid) instead of O(32)
+        constexpr bool COMPACT = CULL && STP_HIER_COMPACT;
+        const uint32_t vm0 = __ballot_sync(hmask, e_id[0] >= 0) >> (half * 16);
+        const uint32_t vm1 = __ballot_sync(hmask, e_id[1] >= 0) >> (half * 16);
+        const int n0 = __popc(vm0), n_valid = n0 + __popc(vm1);
+        int cpos[2] = {hl, hl + 16};
+        if constexpr (COMPACT) {
+            cpos[0] = __popc(vm0 & ((1u << hl) - 1u));
+            cpos[1] = n0 + __popc(vm1 & ((1u << hl) - 1u));
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (!COMPACT || e_id[s] >= 0) {
+                nwd[cpos[s]] = e_d[s];
+                nwi[cpos[s]] = e_id[s];
+            }
         }
         // my resident entries (positions hl, hl+16 of the resident run) before anything is overwritten
         float r_d[2];
@@ -437,29 +505,41 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             r_id[s] = (k < tcount) ? ti[tbase + k] : -1;
         }
         __syncwarp(hmask);
-        const int n_valid = __popc(__ballot_sync(hmask, e_id[0] >= 0)) + __popc(__ballot_sync(hmask, e_id[1] >= 0));
         // ranks: new entry i -> #new before it (depth, then list position) + #resident <= it;
         //        resident k -> k + #new < it
         int rk_new[2] = {0, 0}, sh_res[2] = {0, 0};
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-            const float dj = nwd[j];
+        if constexpr (COMPACT) {
+#pragma unroll 4
+            for (int j = 0; j < n_valid; ++j) {
+                const float dj = nwd[j];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int i = hl + 16 * s;
-                rk_new[s] += (dj < e_d[s]) || (dj == e_d[s] && j < i);
-                sh_res[s] += dj < r_d[s];
+                for (int s = 0; s < 2; ++s) {
+                    rk_new[s] += (dj < e_d[s]) || (dj == e_d[s] && j < cpos[s]);
+                    sh_res[s] += dj < r_d[s];
+                }
+            }
+        } else {
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const float dj = nwd[j];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    rk_new[s] += (dj < e_d[s]) || (dj == e_d[s] && j < cpos[s]);
+                    sh_res[s] += dj < r_d[s];
+                }
             }
         }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            // binary search: number of resident entries with depth <= e_d[s]
-            int lo = 0, hi_ = tcount;
-            while (lo < hi_) {
-                const int mid = (lo + hi_) >> 1;
-                if (td[tbase + mid] <= e_d[s]) lo = mid + 1; else hi_ = mid;
+            if (e_id[s] >= 0) {
+                // binary search: number of resident entries with depth <= e_d[s]
+                int lo = 0, hi_ = tcount;
+                while (lo < hi_) {
+                    const int mid = (lo + hi_) >> 1;
+                    if (td[tbase + mid] <= e_d[s]) lo = mid + 1; else hi_ = mid;
+                }
+                rk_new[s] += lo;
             }
-            rk_new[s] += lo;
         }
         __syncwarp(hmask);
 #pragma unroll
@@ -478,46 +558,49 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         tcount += n_valid;
         __syncwarp(hmask);
 
-        // pop the 16 smallest while more than 32 are held (at most twice, :827-846)
+        // pop the 16 smallest while more than 32 are held (at most twice, :827-846).  The popped ids are handed to the
+        // mid stage through a per-block FIFO: which entries leave the tail, and in which order, does not depend on
+        // anything downstream, so the mid / head work of the two blocks of this warp can be deferred until BOTH have a
+        // group to process and then runs convergently (with 4x4 culling the two tails fill at different times; pushing
+        // each pop through mid and head at once would leave the other half-warp idle).
 #pragma unroll 1
         for (int rep = 0; rep < 2; ++rep) {
             if (tcount > 32) {
-#if !STP_HIER_MIDBATCH
+#if STP_HIER_FIFO
+                ff[((fhead + fcount) * 4 + hl) & (kFifoIds - 1)] = ti[tbase + hl];
+                fcount += 4;
+#else
 #pragma unroll 1
                 for (int g = 0; g < 4; ++g) {
                     const int id_g = ti[tbase + 4 * g + p];
                     mid_push_group(id_g, mid_depth(id_g));
-                }
-#else
-                int gid[4];
-                float gd[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) gid[g] = ti[tbase + 4 * g + p];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) gd[g] = mid_depth(gid[g]);
-#pragma unroll 1
-                for (int g = 0; g < 4; ++g) {
-                    // runtime-indexed pick without local memory
-                    const int id_g = g == 0 ? gid[0] : g == 1 ? gid[1] : g == 2 ? gid[2] : gid[3];
-                    const float d_g = g == 0 ? gd[0] : g == 1 ? gd[1] : g == 2 ? gd[2] : gd[3];
-                    mid_push_group(id_g, d_g);
                 }
 #endif
                 tbase += 16;
                 tcount -= 16;
             }
         }
+#if STP_HIER_FIFO
+        __syncwarp();
+        consume(kFifoLimit);
+#endif
     }
 
     // ---- drain: tail -> mid -> head (:855-925) ---------------------------------------------------------------------------
-    if (__any_sync(hmask, active)) {
-        while (tcount > 0) {
+    consume(-1);
+    const bool half_alive = __any_sync(hmask, active);
+    if (!half_alive) tcount = 0;
+    while (__any_sync(0xffffffffu, tcount > 0)) {
+        if (tcount > 0) {
             const int did = p < tcount ? ti[tbase + p] : -1;
             mid_push_group(did, mid_depth(did));
             tbase += 4;
             tcount -= min(tcount, 4);
         }
-        while (mcount > 0) {
+    }
+    if (!half_alive) mcount = 0;
+    while (__any_sync(0xffffffffu, mcount > 0)) {
+        if (mcount > 0) {
             __syncwarp(qmask);
             const int v = mi[mbase + p];
             __syncwarp(qmask);
@@ -527,8 +610,8 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             mcount -= 4;
             quad_to_head();
         }
-        while (active && hcount > 0) blend_one();
     }
+    while (active && hcount > 0) blend_one();
 
     if constexpr (!BWD) {
         if (inside) {
@@ -544,7 +627,7 @@ template <int HEAD, int MID, bool BWD>
 cudaError_t launch_variant(const Frame& f, bool cull, const RenderArgs& a, const RenderBwdArgs& ab, cudaStream_t stream) {
     dim3 grid(f.grid_x, f.row1 - f.row0, 1);
     if (grid.y == 0) return cudaSuccess;
-    const size_t smem = sizeof(HierShared<MID>);
+    const size_t smem = sizeof(HierShared<MID>) + (BWD ? sizeof(HierSharedBwd) : 0);
     if (cull) {
         cudaFuncSetAttribute(render_hier_kernel<HEAD, MID, true, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         render_hier_kernel<HEAD, MID, true, BWD><<<grid, 256, smem, stream>>>(f, a, ab);
