@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define STP_ABI_VERSION 1
+#define STP_ABI_VERSION 2
 
 /* replaces: enum SortMode / GlobalSortOrder, rasterizer.h:27-41 */
 enum { STP_SORT_GLOBAL = 0, STP_SORT_PPX_FULL = 1, STP_SORT_PPX_KBUFFER = 2, STP_SORT_HIER = 3 };
@@ -58,6 +58,10 @@ typedef struct StpSettings {
     int32_t hierarchical_4x4_culling;
     int32_t load_balancing;   /* scheduling hint only: results never depend on it */
     int32_t proper_ewa_scaling;
+    /* not part of the reference's settings: HIER mode only, blend records per pixel kept by the forward pass for the
+     * backward pass (8 B each, in the image arena; stp_image_bytes).  0 = none: backward repeats the re-sort.
+     * Must have the same value in stp_forward and the matching stp_backward. */
+    int32_t blend_record_cap;
 } StpSettings;
 
 /* replaces: std::function<char*(size_t)> geometryBuffer/binningBuffer/imageBuffer,
@@ -151,7 +155,7 @@ typedef struct StpImageView {
 
 size_t stp_geometry_bytes(int P, int requires_cov3D_inv);
 size_t stp_binning_bytes(int R);
-size_t stp_image_bytes(int width, int height);
+size_t stp_image_bytes(int width, int height, int blend_record_cap);
 int stp_view_geometry(char* geom_buffer, int P, int requires_cov3D_inv, StpGeometryView* out);
 int stp_view_binning(char* binning_buffer, int R, StpBinningView* out);
 int stp_view_image(char* image_buffer, int width, int height, StpImageView* out);

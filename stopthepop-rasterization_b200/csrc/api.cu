@@ -62,6 +62,7 @@ bool convert_settings(const StpSettings* in, Settings& s, std::string& err, bool
     s.tile_based_culling = in->tile_based_culling != 0;
     s.hier_culling = in->hierarchical_4x4_culling != 0;
     s.proper_ewa_scaling = in->proper_ewa_scaling != 0;
+    s.rec_cap = (in->sort_mode == STP_SORT_HIER && in->blend_record_cap > 0) ? in->blend_record_cap : 0;
     if (s.sort_mode == STP_SORT_HIER) {
         // instantiated queue sizes, forward.cu:445-480 / backward.cu:739-767
         if (s.q_mid != 8 && s.q_mid != 12 && s.q_mid != 20) {
@@ -215,8 +216,8 @@ int stp_requires_cov3D_inv(const StpSettings* s) {
 
 size_t stp_geometry_bytes(int P, int inv) { return required<GeometryState>((size_t)P, inv != 0); }
 size_t stp_binning_bytes(int R) { return required<BinningState>((size_t)R); }
-size_t stp_image_bytes(int W, int H) {
-    return required<ImageState>((size_t)W * H, (size_t)((W + 15) / 16) * ((H + 15) / 16));
+size_t stp_image_bytes(int W, int H, int rec_cap) {
+    return required<ImageState>((size_t)W * H, (size_t)((W + 15) / 16) * ((H + 15) / 16), rec_cap > 0 ? rec_cap : 0);
 }
 
 int stp_view_geometry(char* buf, int P, int inv, StpGeometryView* out) {
@@ -245,7 +246,7 @@ int stp_view_binning(char* buf, int R, StpBinningView* out) {
 int stp_view_image(char* buf, int W, int H, StpImageView* out) {
     if (buf == nullptr || out == nullptr) return fail(STP_ERR_INVALID_ARGUMENT, "null argument");
     char* p = buf;
-    ImageState s = ImageState::from_chunk(p, (size_t)W * H, (size_t)((W + 15) / 16) * ((H + 15) / 16));
+    ImageState s = ImageState::from_chunk(p, (size_t)W * H, (size_t)((W + 15) / 16) * ((H + 15) / 16), 0);
     out->final_T = s.final_T;
     out->n_contrib = s.n_contrib;
     out->ranges = reinterpret_cast<uint32_t*>(s.ranges);
@@ -290,9 +291,9 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     char* gp = geom_alloc(geom_user, required<GeometryState>((size_t)P, inv));
     if (!gp) return fail(STP_ERR_ALLOC, "geometry arena allocation failed");
     GeometryState g = GeometryState::from_chunk(gp, (size_t)P, inv);
-    char* ip = image_alloc(image_user, required<ImageState>((size_t)width * height, (size_t)tiles));
+    char* ip = image_alloc(image_user, required<ImageState>((size_t)width * height, (size_t)tiles, s.rec_cap));
     if (!ip) return fail(STP_ERR_ALLOC, "image arena allocation failed");
-    ImageState img = ImageState::from_chunk(ip, (size_t)width * height, (size_t)tiles);
+    ImageState img = ImageState::from_chunk(ip, (size_t)width * height, (size_t)tiles, s.rec_cap);
 
     PreprocessArgs pa;
     pa.P = P; pa.D = D; pa.M = M;
@@ -344,6 +345,9 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     ra.final_T = img.final_T;
     ra.n_contrib = img.n_contrib;
     ra.out_color = out_color;
+    ra.blend_rec = img.blend_rec;
+    ra.tile_flags = img.tile_flags;
+    ra.rec_cap = s.rec_cap;
     if (s.sort_mode == STP_SORT_GLOBAL) {
         STP_CUDA(launch_render_global_fwd(f, ra, stream), "render (GLOBAL)");
     } else if (s.sort_mode == STP_SORT_PPX_KBUFFER) {
@@ -387,7 +391,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     char* bp = binning_buffer;
     BinningState b = BinningState::from_chunk(bp, (size_t)R);
     char* ip = image_buffer;
-    ImageState img = ImageState::from_chunk(ip, (size_t)width * height, (size_t)tiles);
+    ImageState img = ImageState::from_chunk(ip, (size_t)width * height, (size_t)tiles, s.rec_cap);
 
     RenderBwdArgs ra;
     ra.ranges = img.ranges;
@@ -404,6 +408,9 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     ra.dL_dconic = dL_dconic;
     ra.dL_dopacity = dL_dopacity;
     ra.dL_dcolor = dL_dcolor;
+    ra.blend_rec = img.blend_rec;
+    ra.tile_flags = img.tile_flags;
+    ra.rec_cap = s.rec_cap;
     if (R > 0) {
         if (s.sort_mode == STP_SORT_GLOBAL) {
             STP_CUDA(launch_render_global_bwd(f, ra, stream), "render backward (GLOBAL)");
@@ -413,7 +420,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
             STP_CUDA(launch_render_hier_bwd(f, s, ra, stream), "render backward (HIER)");
         }
     }
-    g_launches += (R > 0);
+    g_launches += (R > 0) * ((s.sort_mode == STP_SORT_HIER && s.rec_cap > 0) ? 2 : 1);
     timer.mark("RenderBackward");
 
     PreprocessBwdArgs pa;

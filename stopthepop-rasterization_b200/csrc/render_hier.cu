@@ -142,6 +142,12 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     const uint32_t pix_id = (uint32_t)f.W * py + px;
     const float pxf = (float)px, pyf = (float)py;
     const size_t plane = (size_t)f.W * f.H;
+    const int tile_lin = tile_y * f.grid_x + tile_x;
+    if constexpr (BWD) {
+        // with a blend log the replay kernel has already handled every pixel whose log is complete: this kernel only
+        // re-sorts tiles that contain a pixel with more blends than the log holds, and only for those pixels
+        if (ab.blend_rec != nullptr && ab.tile_flags[tile_lin] == 0u) return;
+    }
 
     const uint2* __restrict__ ranges = BWD ? ab.ranges : a.ranges;
     const uint32_t* __restrict__ point_list = BWD ? ab.point_list : a.point_list;
@@ -186,6 +192,10 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     }
     const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
     bool active = inside;
+    if constexpr (BWD) {
+        if (ab.blend_rec != nullptr) active = inside && ab.n_contrib[pix_id] > (uint32_t)ab.rec_cap;
+    }
+    int nrec = 0;  // forward: blends of this pixel so far (= position in its blend log)
 
     // head queue: sorted by depth, hd[0] is the next to blend
     float hd[HEAD], hs[HEAD];
@@ -214,6 +224,11 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             ps.C1 = ffma(fmul(__ldg(colors + 3 * id + 1), alpha), ps.T, ps.C1);
             ps.C2 = ffma(fmul(__ldg(colors + 3 * id + 2), alpha), ps.T, ps.C2);
             ps.T = test_T;
+            if (a.blend_rec != nullptr) {
+                if (nrec < a.rec_cap)
+                    a.blend_rec[((size_t)tile_lin * a.rec_cap + nrec) * 256 + tid] = make_uint2((uint32_t)id, __float_as_uint(alpha));
+                ++nrec;
+            }
         } else {
             const float G = hs[0];
             const float4 co = __ldg(conic_opacity + id);
@@ -619,7 +634,75 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             a.out_color[pix_id] = ffma(ps.T, f.background[0], ps.C0);
             a.out_color[plane + pix_id] = ffma(ps.T, f.background[1], ps.C1);
             a.out_color[2 * plane + pix_id] = ffma(ps.T, f.background[2], ps.C2);
+            if (a.blend_rec != nullptr) {
+                a.n_contrib[pix_id] = (uint32_t)nrec;
+                if (nrec > a.rec_cap) atomicOr(a.tile_flags + tile_lin, 1u);
+            }
         }
+    }
+}
+
+// ---- backward by replay: every pixel walks its own blend log (front to back, like the reference's hierarchical backward
+// :1071-1170) and accumulates the gradients of the logged Gaussians.  Same arithmetic as the BWD branch of blend_one
+// above; G is recovered from the logged alpha (alpha / opacity; re-evaluated with expf when alpha was clamped to 0.99).
+__global__ void __launch_bounds__(256)
+render_hier_replay_bwd_kernel(Frame f, RenderBwdArgs a) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = lane >> 4, hl = lane & 15;
+    const int b = warp * 2 + half, q = hl >> 2, p = hl & 3;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
+    const int cx = tile_x * 16 + (b & 3) * 4, cy = tile_y * 16 + (b >> 2) * 4;
+    const int px = cx + (q & 1) * 2 + (p & 1), py = cy + (q >> 1) * 2 + (p >> 1);
+    if (px >= f.W || py >= f.H) return;
+    const uint32_t pix_id = (uint32_t)f.W * py + px;
+    const uint32_t n = a.n_contrib[pix_id];
+    if (n == 0u || n > (uint32_t)a.rec_cap) return;
+    const float pxf = (float)px, pyf = (float)py;
+    const size_t plane = (size_t)f.W * f.H;
+    const int tile_lin = tile_y * f.grid_x + tile_x;
+    const float T_final = a.final_T[pix_id];
+    const float g0 = a.dL_dpix[pix_id], g1 = a.dL_dpix[plane + pix_id], g2 = a.dL_dpix[2 * plane + pix_id];
+    const float f0 = a.pixel_colors[pix_id] - T_final * f.background[0];
+    const float f1 = a.pixel_colors[plane + pix_id] - T_final * f.background[1];
+    const float f2 = a.pixel_colors[2 * plane + pix_id] - T_final * f.background[2];
+    const float bg_dot = f.background[0] * g0 + f.background[1] * g1 + f.background[2] * g2;
+    const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
+    const uint2* __restrict__ rec = a.blend_rec + (size_t)tile_lin * a.rec_cap * 256 + tid;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint2 nxt = rec[0];
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint2 cur = nxt;
+        if (k + 1 < n) nxt = rec[(size_t)(k + 1) * 256];
+        const int id = (int)cur.x;
+        const float alpha = __uint_as_float(cur.y);
+        const float4 co = __ldg(a.conic_opacity + id);
+        const float2 xy = __ldg(a.means2D + id);
+        const float c0 = __ldg(a.colors + 3 * id + 0), c1 = __ldg(a.colors + 3 * id + 1), c2 = __ldg(a.colors + 3 * id + 2);
+        const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
+        const float G = (alpha < 0.99f) ? alpha / co.w : expf(gaussian_power(dx, dy, co.x, co.y, co.z));
+        const float test_T = fmul(T, fsub(1.0f, alpha));
+        const float dchannel_dcolor = alpha * T;
+        C0 += c0 * alpha * T;
+        C1 += c1 * alpha * T;
+        C2 += c2 * alpha * T;
+        const float inv_T = 1.0f / test_T;
+        float dL_dalpha = (c0 - (f0 - C0) * inv_T) * g0 + (c1 - (f1 - C1) * inv_T) * g1 + (c2 - (f2 - C2) * inv_T) * g2;
+        dL_dalpha *= T;
+        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+        const float dL_dG = co.w * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        const float dG_ddelx = -gdx * co.x - gdy * co.y;
+        const float dG_ddely = -gdy * co.z - gdx * co.y;
+        atomicAdd(a.dL_dcolor + 3 * id + 0, dchannel_dcolor * g0);
+        atomicAdd(a.dL_dcolor + 3 * id + 1, dchannel_dcolor * g1);
+        atomicAdd(a.dL_dcolor + 3 * id + 2, dchannel_dcolor * g2);
+        atomicAdd(a.dL_dmean2D + 3 * id + 0, dL_dG * dG_ddelx * ddelx_dx);
+        atomicAdd(a.dL_dmean2D + 3 * id + 1, dL_dG * dG_ddely * ddely_dy);
+        atomicAdd(a.dL_dconic + 4 * id + 0, -0.5f * gdx * dx * dL_dG);
+        atomicAdd(a.dL_dconic + 4 * id + 1, -0.5f * gdx * dy * dL_dG);
+        atomicAdd(a.dL_dconic + 4 * id + 3, -0.5f * gdy * dy * dL_dG);
+        atomicAdd(a.dL_dopacity + id, G * dL_dalpha);
+        T = test_T;
     }
 }
 
@@ -663,12 +746,23 @@ cudaError_t dispatch(const Frame& f, const Settings& s, const RenderArgs& a, con
 
 cudaError_t launch_render_hier_fwd(const Frame& f, const Settings& s, const RenderArgs& a, cudaStream_t stream) {
     RenderBwdArgs dummy{};
+    if (a.blend_rec != nullptr) {
+        cudaError_t e = cudaMemsetAsync(a.tile_flags, 0, sizeof(uint32_t) * (size_t)f.grid_x * f.grid_y, stream);
+        if (e != cudaSuccess) return e;
+    }
     return dispatch<false>(f, s, a, dummy, stream);
 }
 
 cudaError_t launch_render_hier_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream) {
     RenderArgs dummy{};
-    return dispatch<true>(f, s, dummy, a, stream);
+    if (a.blend_rec != nullptr) {
+        dim3 grid(f.grid_x, f.row1 - f.row0, 1);
+        if (grid.y == 0) return cudaSuccess;
+        render_hier_replay_bwd_kernel<<<grid, 256, 0, stream>>>(f, a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return dispatch<true>(f, s, dummy, a, stream);  // re-sorting backward: everything, or only the pixels whose log overflowed
 }
 
 }  // namespace stp

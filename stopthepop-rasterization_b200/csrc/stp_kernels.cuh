@@ -30,6 +30,9 @@ struct RenderArgs {
     float* final_T;
     uint32_t* n_contrib;
     float* out_color;
+    uint2* blend_rec;      // HIER blend log (nullptr = do not record)
+    uint32_t* tile_flags;
+    int rec_cap;
 };
 
 struct RenderBwdArgs {
@@ -47,6 +50,9 @@ struct RenderBwdArgs {
     float* dL_dconic;    // [P,4]
     float* dL_dopacity;  // [P]
     float* dL_dcolor;    // [P,3]
+    const uint2* blend_rec;  // HIER blend log written by the forward pass (nullptr = re-sort everything)
+    const uint32_t* tile_flags;
+    int rec_cap;
 };
 
 struct PreprocessBwdArgs {

@@ -62,7 +62,14 @@ struct ImageState {
     uint32_t* tile_count;
     uint32_t* tile_cursor;
     uint32_t* large_tiles;
-    static ImageState from_chunk(char*& chunk, size_t N, size_t tiles) {
+    // HIER blend records (render_hier.cu): the forward pass logs every blend of every pixel, (Gaussian id, alpha), at
+    // [tile][k][thread]; the backward pass replays the log instead of repeating the hierarchical re-sort.  n_contrib
+    // holds the number of blends per pixel (the reference leaves it unwritten in HIER mode); pixels with more than
+    // rec_cap blends set tile_flags and are handled by the re-sorting backward kernel.
+    uint32_t* tile_flags;
+    uint2* blend_rec;  // nullptr when rec_cap == 0
+    int rec_cap;
+    static ImageState from_chunk(char*& chunk, size_t N, size_t tiles, int rec_cap) {
         ImageState s;
         obtain(chunk, s.final_T, N);
         obtain(chunk, s.n_contrib, N);
@@ -70,6 +77,10 @@ struct ImageState {
         obtain(chunk, s.tile_count, tiles);
         obtain(chunk, s.tile_cursor, tiles);
         obtain(chunk, s.large_tiles, tiles);
+        obtain(chunk, s.tile_flags, tiles);
+        s.blend_rec = nullptr;
+        s.rec_cap = rec_cap;
+        if (rec_cap > 0) obtain(chunk, s.blend_rec, tiles * 256 * (size_t)rec_cap);
         return s;
     }
 };
@@ -118,6 +129,7 @@ struct Settings {
     int sort_mode, sort_order;
     int q_mid, q_head;
     bool rect_bounding, tight_opacity_bounding, tile_based_culling, hier_culling, proper_ewa_scaling;
+    int rec_cap;  // blend records per pixel (HIER, 0 = none)
     bool per_tile_depth() const { return sort_order == 2 || sort_order == 3; }
     bool requires_inv() const { return sort_mode != 0 || per_tile_depth(); }
 };

@@ -34,7 +34,7 @@ class StpSettings(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "sort_mode", "sort_order", "queue_tile_4x4", "queue_tile_2x2", "queue_per_pixel", "rect_bounding",
         "tight_opacity_bounding", "tile_based_culling", "hierarchical_4x4_culling", "load_balancing",
-        "proper_ewa_scaling")]
+        "proper_ewa_scaling", "blend_record_cap")]
 
 
 class StpTileBand(ctypes.Structure):
@@ -64,7 +64,7 @@ _lib.stp_geometry_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
 _lib.stp_binning_bytes.restype = ctypes.c_size_t
 _lib.stp_binning_bytes.argtypes = [ctypes.c_int]
 _lib.stp_image_bytes.restype = ctypes.c_size_t
-_lib.stp_image_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+_lib.stp_image_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
 _lib.stp_requires_cov3D_inv.argtypes = [ctypes.POINTER(StpSettings)]
 _lib.stp_view_geometry.argtypes = [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(StpGeometryView)]
 _lib.stp_view_binning.argtypes = [_P, ctypes.c_int, ctypes.POINTER(StpBinningView)]
@@ -94,7 +94,7 @@ _lib.stp_backward.argtypes = [
     _P, _P, _P, _P, _P, _P, _P, _P, _P,  # 9 grads
     ctypes.c_int, _P]
 
-if _lib.stp_abi_version() != 1:
+if _lib.stp_abi_version() != 2:
     raise ImportError("libstp_rasterizer.so ABI version mismatch")
 
 LIBRARY_PATH = _LIB_PATH
@@ -104,7 +104,12 @@ def _err():
     return _lib.stp_last_error().decode("utf-8", "replace")
 
 
-def settings_from_dict(d):
+# HIER mode: blends logged per pixel by a forward pass that will be followed by a backward pass (8 B each; the image
+# arena grows by 2 KB per pixel at the default).  Pixels that blend more fall back to the re-sorting backward kernel.
+BLEND_RECORD_CAP = int(os.environ.get("STP_BLEND_RECORD_CAP", "256"))
+
+
+def settings_from_dict(d, blend_record_cap=0):
     """dict produced by ExtendedSettings.to_dict() -> StpSettings; every key mandatory like the
     reference's from_json (rasterizer.h:160-182 uses .at())."""
     ss, cs = d["sort_settings"], d["culling_settings"]
@@ -112,7 +117,8 @@ def settings_from_dict(d):
     return StpSettings(int(ss["sort_mode"]), int(ss["sort_order"]), int(q["tile_4x4"]), int(q["tile_2x2"]),
                        int(q["per_pixel"]), int(bool(cs["rect_bounding"])), int(bool(cs["tight_opacity_bounding"])),
                        int(bool(cs["tile_based_culling"])), int(bool(cs["hierarchical_4x4_culling"])),
-                       int(bool(d["load_balancing"])), int(bool(d["proper_ewa_scaling"])))
+                       int(bool(d["load_balancing"])), int(bool(d["proper_ewa_scaling"])),
+                       int(blend_record_cap) if int(ss["sort_mode"]) == 3 else 0)
 
 
 def _ptr(t):
@@ -155,7 +161,10 @@ def _stream(device):
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
-                        degree, campos, prefiltered, settings_dict, render_depth, debug, tile_band=None):
+                        degree, campos, prefiltered, settings_dict, render_depth, debug, tile_band=None,
+                        record_blends=True):
+    """record_blends (HIER mode only): keep the per-pixel blend log that lets the backward pass skip the hierarchical
+    re-sort; pass False for inference-only calls (GaussianRasterizer does, when no input requires a gradient)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:68-71
     if render_depth:
@@ -165,7 +174,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
     radii = torch.zeros((P,), dtype=torch.int32, device=device)
     geom, binning, img = _Arena(device), _Arena(device), _Arena(device)
-    st = settings_from_dict(settings_dict)
+    st = settings_from_dict(settings_dict, BLEND_RECORD_CAP if record_blends else 0)
     if P == 0:
         return 0, out_color, radii, geom.tensor, binning.tensor, img.tensor
     means3D = _f32(means3D, device)
@@ -196,7 +205,7 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)  # rasterize_points.cu:169-170
     M = sh.size(1) if sh is not None and sh.numel() != 0 else 0
-    st = settings_from_dict(settings_dict)
+    st = settings_from_dict(settings_dict, blend_record_cap_of(imageBuffer, W, H))
     # ONE slab instead of nine torch::zeros (rasterize_points.cu:178-186).  Only the four atomically accumulated
     # arrays (opacity, means2D, colors, conic: 44 B/Gaussian) are cleared; every row of the other five is written by
     # the preprocess-backward kernel (zeros for culled Gaussians), so 256 B/Gaussian of memset disappear.  The five
@@ -234,6 +243,13 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
     grads8 = (dL_dmeans2D.view(P, 3), dL_dcolors.view(P, NUM_CHANNELS), dL_dopacity.view(P, 1), dL_dmeans3D.view(P, 3),
               dL_dcov3D.view(P, 6), dL_dsh.view(P, M, 3), dL_dscales.view(P, 3), dL_drot.view(P, 4))
     return (grads8, param_slab) if want_param_slab else grads8
+
+
+def blend_record_cap_of(imageBuffer, W, H):
+    """blend-log capacity the forward pass allocated inside this image arena (0 = none), from its size."""
+    extra = imageBuffer.numel() - _lib.stp_image_bytes(W, H, 0)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    return max(0, extra) // (tiles * 256 * 8)
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

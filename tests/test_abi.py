@@ -47,7 +47,7 @@ def test_abi_version_and_arena_sizes(lib):
     lib.stp_geometry_bytes.restype = ctypes.c_size_t
     lib.stp_geometry_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.stp_image_bytes.restype = ctypes.c_size_t
-    lib.stp_image_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.stp_image_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.stp_binning_bytes.restype = ctypes.c_size_t
     lib.stp_binning_bytes.argtypes = [ctypes.c_int]
     P = 1000
@@ -55,7 +55,9 @@ def test_abi_version_and_arena_sizes(lib):
     # we do not keep (slots are claimed per tile, binning.cu), +48 B with the inverse covariance
     g0, g1 = lib.stp_geometry_bytes(P, 0), lib.stp_geometry_bytes(P, 1)
     assert g0 >= 79 * P and g1 - g0 >= 48 * P and g1 - g0 < 48 * P + 512
-    assert lib.stp_image_bytes(1920, 1080) >= 8 * 1920 * 1080 + 8 * 120 * 68
+    assert lib.stp_image_bytes(1920, 1080, 0) >= 8 * 1920 * 1080 + 8 * 120 * 68
+    # HIER blend log: 8 B per (pixel of a whole tile, record)
+    assert lib.stp_image_bytes(1920, 1080, 16) - lib.stp_image_bytes(1920, 1080, 0) >= 120 * 68 * 256 * 16 * 8
     assert lib.stp_binning_bytes(10) >= 28 * 10  # point_list + sorted keys + bucket + merge scratch
     assert lib.stp_binning_bytes(0) > 0
 
