@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define STP_ABI_VERSION 2
+#define STP_ABI_VERSION 3
 
 /* replaces: enum SortMode / GlobalSortOrder, rasterizer.h:27-41 */
 enum { STP_SORT_GLOBAL = 0, STP_SORT_PPX_FULL = 1, STP_SORT_PPX_KBUFFER = 2, STP_SORT_HIER = 3 };
@@ -103,10 +103,12 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user,
 
 /* replaces: CudaRasterizer::Rasterizer::backward, rasterizer.h:222-257 (impl rasterizer_impl.cu:417-526)
  * as called by RasterizeGaussiansBackwardCUDA, rasterize_points.cu:141-232.
- * The four atomically accumulated outputs dL_dmean2D [P,3], dL_dconic [P,2,2], dL_dopacity [P,1], dL_dcolor [P,3]
- * must be zero-filled by the caller (torch::zeros, rasterize_points.cu:178-186).  dL_dmean3D [P,3], dL_dcov3D [P,6],
- * dL_dsh [P,M,3], dL_dscale [P,3], dL_drot [P,4] may be uninitialised: every row is written (zeros for culled
- * Gaussians), which removes 256 B/Gaussian of memset per iteration.
+ * grad_accum [P,12] f32 is the only buffer the caller must zero-fill: the render-backward kernels accumulate the
+ * screen-space gradients there, packed for 128-bit vector reductions ({conic.x, conic.y, conic.w, opacity | mean2D.x,
+ * mean2D.y, color.r, color.g | color.b}; the reference zero-fills nine separate tensors, rasterize_points.cu:178-186).
+ * All dL_* arrays are pure outputs and may be uninitialised -- every row is written, zeros for culled Gaussians:
+ * dL_dmean2D [P,3], dL_dopacity [P,1], dL_dcolor [P,3], dL_dmean3D [P,3], dL_dcov3D [P,6], dL_dsh [P,M,3],
+ * dL_dscale [P,3], dL_drot [P,4].
  */
 int stp_backward(int P, int D, int M, int R,
                  const float* background, int width, int height,
@@ -119,7 +121,7 @@ int stp_backward(int P, int D, int M, int R,
                  const float* pixel_colors, const int* radii,
                  char* geom_buffer, char* binning_buffer, char* image_buffer,
                  const float* dL_dpix,
-                 float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                 float* dL_dmean2D, float* grad_accum, float* dL_dopacity, float* dL_dcolor,
                  float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                  int debug, void* stream);
 

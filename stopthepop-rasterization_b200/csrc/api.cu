@@ -369,7 +369,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
                  const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
                  const float* inv_viewprojmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
                  const float* pixel_colors, const int* radii, char* geom_buffer, char* binning_buffer,
-                 char* image_buffer, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                 char* image_buffer, const float* dL_dpix, float* dL_dmean2D, float* grad_accum, float* dL_dopacity,
                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                  int debug, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -404,10 +404,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     ra.n_contrib = img.n_contrib;
     ra.pixel_colors = pixel_colors;
     ra.dL_dpix = dL_dpix;
-    ra.dL_dmean2D = dL_dmean2D;
-    ra.dL_dconic = dL_dconic;
-    ra.dL_dopacity = dL_dopacity;
-    ra.dL_dcolor = dL_dcolor;
+    ra.grad_accum = grad_accum;
     ra.blend_rec = img.blend_rec;
     ra.tile_flags = img.tile_flags;
     ra.rec_cap = s.rec_cap;
@@ -429,7 +426,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     pa.scales = scales; pa.rotations = rotations; pa.scale_modifier = scale_modifier;
     pa.cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
     pa.proper_ewa_scaling = s.proper_ewa_scaling;
-    pa.dL_dmean2D = dL_dmean2D; pa.dL_dconic = dL_dconic; pa.dL_dopacity = dL_dopacity;
+    pa.dL_dmean2D = dL_dmean2D; pa.grad_accum = grad_accum; pa.dL_dopacity = dL_dopacity;
     pa.dL_dmean3D = dL_dmean3D; pa.dL_dcolor = dL_dcolor; pa.dL_dcov3D = dL_dcov3D; pa.dL_dsh = dL_dsh;
     pa.dL_dscale = dL_dscale; pa.dL_drot = dL_drot;
     STP_CUDA(launch_preprocess_bwd(pa, f, stream), "preprocess backward");

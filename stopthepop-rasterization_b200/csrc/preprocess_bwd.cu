@@ -87,12 +87,17 @@ preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
     const int warp_base = blockIdx.x * blockDim.x + warp * 32;
     const int rows = min(32, a.P - warp_base);
     const bool has_sh = a.shs != nullptr && n_sh > 0;
-    // Every row of dL_dmean3D / dL_dcov3D / dL_dscale / dL_drot / dL_dsh is written here: culled Gaussians get
+    // Every row of every output (dL_dmean2D / dL_dcolor / dL_dopacity included) is written here: culled Gaussians get
     // zeros, so the caller does not have to clear these buffers (the reference memsets 256 B per Gaussian per
     // iteration for them, rasterize_points.cu:178-186).
     if (valid && !alive) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) a.dL_dmean3D[3 * idx + k] = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            a.dL_dmean3D[3 * idx + k] = 0.f;
+            a.dL_dmean2D[3 * idx + k] = 0.f;
+            a.dL_dcolor[3 * idx + k] = 0.f;
+        }
+        a.dL_dopacity[idx] = 0.f;
 #pragma unroll
         for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * idx + k] = 0.f;
         if (a.scales != nullptr) {
@@ -149,7 +154,18 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
     for (int k = 0; k < 6; ++k) c3[k] = a.cov3D[6 * idx + k];
 
     // ---------------- conic -> cov2D -> cov3D / mean (computeCov2DCUDA) ----------------
-    const float dcon_x = a.dL_dconic[4 * idx], dcon_y = a.dL_dconic[4 * idx + 1], dcon_z = a.dL_dconic[4 * idx + 3];
+    // packed screen-space gradients of this Gaussian (stp_kernels.cuh: kGradAccum layout)
+    const float4 acc0 = reinterpret_cast<const float4*>(a.grad_accum)[3 * idx];
+    const float4 acc1 = reinterpret_cast<const float4*>(a.grad_accum)[3 * idx + 1];
+    const float acc_cb = a.grad_accum[kGradAccumFloats * idx + 8];
+    const float dcon_x = acc0.x, dcon_y = acc0.y, dcon_z = acc0.z;
+    a.dL_dmean2D[3 * idx] = acc1.x;
+    a.dL_dmean2D[3 * idx + 1] = acc1.y;
+    a.dL_dmean2D[3 * idx + 2] = 0.f;
+    a.dL_dcolor[3 * idx] = acc1.z;
+    a.dL_dcolor[3 * idx + 1] = acc1.w;
+    a.dL_dcolor[3 * idx + 2] = acc_cb;
+    a.dL_dopacity[idx] = acc0.w;
     F3 t = {vm[0] * mean.x + vm[4] * mean.y + vm[8] * mean.z + vm[12], vm[1] * mean.x + vm[5] * mean.y + vm[9] * mean.z + vm[13],
             vm[2] * mean.x + vm[6] * mean.y + vm[10] * mean.z + vm[14]};
     const float limx = 1.3f * f.tan_fovx, limy = 1.3f * f.tan_fovy;
@@ -191,7 +207,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
         const float det_plus = c_xx * c_yy - c_xy * c_xy;
         const float ratio = det_cov_orig / det_plus;
         const float h_scaling = sqrtf(fmaxf(0.000025f, ratio));
-        const float dL_dop = a.dL_dopacity[idx];
+        const float dL_dop = acc0.w;
         const float d_h = dL_dop * a.opacities[idx];
         a.dL_dopacity[idx] = dL_dop * h_scaling;
         const float d_inside_root = (ratio <= 0.000025f) ? 0.f : d_h / (2.f * h_scaling);
@@ -249,7 +265,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
         const float m_w = 1.0f / (hw + 0.0000001f);
         const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
         const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
-        const float gx = a.dL_dmean2D[3 * idx], gy = a.dL_dmean2D[3 * idx + 1];
+        const float gx = acc1.x, gy = acc1.y;
         dmean.x += (proj[0] * m_w - proj[3] * mul1) * gx + (proj[1] * m_w - proj[3] * mul2) * gy;
         dmean.y += (proj[4] * m_w - proj[7] * mul1) * gx + (proj[5] * m_w - proj[7] * mul2) * gy;
         dmean.z += (proj[8] * m_w - proj[11] * mul1) * gx + (proj[9] * m_w - proj[11] * mul2) * gy;
@@ -264,7 +280,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
         float* __restrict__ dsh = row ? row : a.dL_dsh + (size_t)idx * a.M * 3;
         const int D = a.D;
         auto sh = [&](int k) { return F3{shp[3 * k], shp[3 * k + 1], shp[3 * k + 2]}; };
-        F3 dRGB = {a.dL_dcolor[3 * idx], a.dL_dcolor[3 * idx + 1], a.dL_dcolor[3 * idx + 2]};
+        F3 dRGB = {acc1.z, acc1.w, acc_cb};
         dRGB.x *= a.clamped[3 * idx + 0] ? 0.f : 1.f;
         dRGB.y *= a.clamped[3 * idx + 1] ? 0.f : 1.f;
         dRGB.z *= a.clamped[3 * idx + 2] ? 0.f : 1.f;

@@ -307,18 +307,13 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
         if (tid < n) {
             const uint32_t id = s_id[tid];
             const float c0 = s_acc[tid][0], c1 = s_acc[tid][1], c2 = s_acc[tid][2];
-            if (c0 != 0.f) atomicAdd(&a.dL_dcolor[3 * id + 0], c0);
-            if (c1 != 0.f) atomicAdd(&a.dL_dcolor[3 * id + 1], c1);
-            if (c2 != 0.f) atomicAdd(&a.dL_dcolor[3 * id + 2], c2);
             const float m0 = s_acc[tid][3], m1 = s_acc[tid][4];
-            if (m0 != 0.f) atomicAdd(&a.dL_dmean2D[3 * id + 0], m0);
-            if (m1 != 0.f) atomicAdd(&a.dL_dmean2D[3 * id + 1], m1);
             const float k0 = s_acc[tid][5], k1 = s_acc[tid][6], k2 = s_acc[tid][7];
-            if (k0 != 0.f) atomicAdd(&a.dL_dconic[4 * id + 0], k0);
-            if (k1 != 0.f) atomicAdd(&a.dL_dconic[4 * id + 1], k1);
-            if (k2 != 0.f) atomicAdd(&a.dL_dconic[4 * id + 3], k2);
             const float o = s_acc[tid][8];
-            if (o != 0.f) atomicAdd(&a.dL_dopacity[id], o);
+            float* const acc = a.grad_accum + (size_t)kGradAccumFloats * id;
+            if (k0 != 0.f || k1 != 0.f || k2 != 0.f || o != 0.f) red_add_v4(acc, k0, k1, k2, o);
+            if (m0 != 0.f || m1 != 0.f || c0 != 0.f || c1 != 0.f) red_add_v4(acc + 4, m0, m1, c0, c1);
+            if (c2 != 0.f) atomicAdd(acc + 8, c2);
         }
     }
 }

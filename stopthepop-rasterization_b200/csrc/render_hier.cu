@@ -255,15 +255,9 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             const float gdx = G * dx, gdy = G * dy;
             const float dG_ddelx = -gdx * co.x - gdy * co.y;
             const float dG_ddely = -gdy * co.z - gdx * co.y;
-            atomicAdd(ab.dL_dcolor + 3 * id + 0, dchannel_dcolor * g0);
-            atomicAdd(ab.dL_dcolor + 3 * id + 1, dchannel_dcolor * g1);
-            atomicAdd(ab.dL_dcolor + 3 * id + 2, dchannel_dcolor * g2);
-            atomicAdd(ab.dL_dmean2D + 3 * id + 0, dL_dG * dG_ddelx * ddelx_dx);
-            atomicAdd(ab.dL_dmean2D + 3 * id + 1, dL_dG * dG_ddely * ddely_dy);
-            atomicAdd(ab.dL_dconic + 4 * id + 0, -0.5f * gdx * dx * dL_dG);
-            atomicAdd(ab.dL_dconic + 4 * id + 1, -0.5f * gdx * dy * dL_dG);
-            atomicAdd(ab.dL_dconic + 4 * id + 3, -0.5f * gdy * dy * dL_dG);
-            atomicAdd(ab.dL_dopacity + id, G * dL_dalpha);
+            accumulate_grads(ab.grad_accum, id, dchannel_dcolor * g0, dchannel_dcolor * g1, dchannel_dcolor * g2,
+                             dL_dG * dG_ddelx * ddelx_dx, dL_dG * dG_ddely * ddely_dy, -0.5f * gdx * dx * dL_dG,
+                             -0.5f * gdx * dy * dL_dG, -0.5f * gdy * dy * dL_dG, G * dL_dalpha);
             ps.T = test_T;
         }
 #pragma unroll
@@ -693,15 +687,9 @@ render_hier_replay_bwd_kernel(Frame f, RenderBwdArgs a) {
         const float gdx = G * dx, gdy = G * dy;
         const float dG_ddelx = -gdx * co.x - gdy * co.y;
         const float dG_ddely = -gdy * co.z - gdx * co.y;
-        atomicAdd(a.dL_dcolor + 3 * id + 0, dchannel_dcolor * g0);
-        atomicAdd(a.dL_dcolor + 3 * id + 1, dchannel_dcolor * g1);
-        atomicAdd(a.dL_dcolor + 3 * id + 2, dchannel_dcolor * g2);
-        atomicAdd(a.dL_dmean2D + 3 * id + 0, dL_dG * dG_ddelx * ddelx_dx);
-        atomicAdd(a.dL_dmean2D + 3 * id + 1, dL_dG * dG_ddely * ddely_dy);
-        atomicAdd(a.dL_dconic + 4 * id + 0, -0.5f * gdx * dx * dL_dG);
-        atomicAdd(a.dL_dconic + 4 * id + 1, -0.5f * gdx * dy * dL_dG);
-        atomicAdd(a.dL_dconic + 4 * id + 3, -0.5f * gdy * dy * dL_dG);
-        atomicAdd(a.dL_dopacity + id, G * dL_dalpha);
+        accumulate_grads(a.grad_accum, id, dchannel_dcolor * g0, dchannel_dcolor * g1, dchannel_dcolor * g2,
+                         dL_dG * dG_ddelx * ddelx_dx, dL_dG * dG_ddely * ddely_dy, -0.5f * gdx * dx * dL_dG,
+                         -0.5f * gdx * dy * dL_dG, -0.5f * gdy * dy * dL_dG, G * dL_dalpha);
         T = test_T;
     }
 }

@@ -94,7 +94,7 @@ _lib.stp_backward.argtypes = [
     _P, _P, _P, _P, _P, _P, _P, _P, _P,  # 9 grads
     ctypes.c_int, _P]
 
-if _lib.stp_abi_version() != 2:
+if _lib.stp_abi_version() != 3:
     raise ImportError("libstp_rasterizer.so ABI version mismatch")
 
 LIBRARY_PATH = _LIB_PATH
@@ -206,19 +206,19 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)  # rasterize_points.cu:169-170
     M = sh.size(1) if sh is not None and sh.numel() != 0 else 0
     st = settings_from_dict(settings_dict, blend_record_cap_of(imageBuffer, W, H))
-    # ONE slab instead of nine torch::zeros (rasterize_points.cu:178-186).  Only the four atomically accumulated
-    # arrays (opacity, means2D, colors, conic: 44 B/Gaussian) are cleared; every row of the other five is written by
-    # the preprocess-backward kernel (zeros for culled Gaussians), so 256 B/Gaussian of memset disappear.  The five
-    # PARAMETER gradients come first and contiguous, so a data-parallel caller can all-reduce them as one buffer
-    # (stp_sharding.py); the per-view intermediates (means2D, colors, conic, cov3D) follow.
-    widths = [3, 3 * M, 3, 4, 1, 3, 3, 4, 6]  # means3D sh scales rot opacity | means2D colors conic | cov3D
+    # ONE slab instead of nine torch::zeros (rasterize_points.cu:178-186).  Only the packed screen-space accumulator
+    # (48 B/Gaussian, include/stp_rasterizer.h) is cleared; every row of the eight outputs is written by the
+    # preprocess-backward kernel (zeros for culled Gaussians).  The five PARAMETER gradients come first and
+    # contiguous, so a data-parallel caller can all-reduce them as one buffer (stp_sharding.py); the per-view
+    # intermediates follow.
+    widths = [3, 3 * M, 3, 4, 1, 3, 3, 6, 12]  # means3D sh scales rot opacity | means2D colors cov3D | accumulator
     flat = torch.empty((sum(widths) * P,), dtype=torch.float32, device=device)
-    flat[sum(widths[:4]) * P:sum(widths[:8]) * P].zero_()
+    flat[sum(widths[:8]) * P:].zero_()
     views, off = [], 0
     for w in widths:
         views.append(flat[off:off + w * P])
         off += w * P
-    dL_dmeans3D, dL_dsh, dL_dscales, dL_drot, dL_dopacity, dL_dmeans2D, dL_dcolors, dL_dconic, dL_dcov3D = views
+    dL_dmeans3D, dL_dsh, dL_dscales, dL_drot, dL_dopacity, dL_dmeans2D, dL_dcolors, dL_dcov3D, grad_accum = views
     param_slab = flat[:sum(widths[:5]) * P]
     if P != 0:
         means3D = _f32(means3D, device)
@@ -235,7 +235,7 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
                                    _ptr(projmatrix), _ptr(inv_viewprojmatrix), _ptr(campos), float(tan_fovx),
                                    float(tan_fovy), _ptr(pixel_colors), _ptr(radii), _ptr(geomBuffer),
                                    _ptr(binningBuffer), _ptr(imageBuffer), _ptr(dL_dout_color), _ptr(dL_dmeans2D),
-                                   _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D),
+                                   _ptr(grad_accum), _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D),
                                    _ptr(dL_dcov3D), _ptr(dL_dsh) if M else None, _ptr(dL_dscales), _ptr(dL_drot),
                                    int(debug), _stream(device))
         if rc != 0:
