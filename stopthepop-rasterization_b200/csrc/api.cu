@@ -286,6 +286,8 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
                          tan_fovy);
     const int tiles = f.grid_x * f.grid_y;
     const bool inv = s.requires_inv();
+    if (s.rec_cap > 0 && (double)tiles * 256.0 * (double)s.rec_cap >= 4294967296.0)
+        return fail(STP_ERR_INVALID_ARGUMENT, "blend_record_cap too large for this image (log is indexed with 32 bits)");
     StageTimer timer((debug & 2) != 0, stream);
 
     char* gp = geom_alloc(geom_user, required<GeometryState>((size_t)P, inv));

@@ -33,6 +33,9 @@
 #ifndef STP_HIER_MINB_FWD  // resident CTAs per SM asked from ptxas (register cap 48 / 64): the kernels are latency bound and
 #define STP_HIER_MINB_FWD 5  // occupancy limited by registers; A/B on B200: fwd 3->5 CTAs -22 %, bwd 3->4 CTAs -10 % (5: worse, spills)
 #endif
+#ifndef STP_HIER_MINB_FWD_CULL  // the 4x4-culling forward variant keeps more state live: 4 CTAs (64 registers) beat 5 there
+#define STP_HIER_MINB_FWD_CULL 4
+#endif
 #ifndef STP_HIER_MINB_BWD
 #define STP_HIER_MINB_BWD 4
 #endif
@@ -121,7 +124,7 @@ struct PixelState<true> {
 };
 
 template <int HEAD, int MID, bool CULL, bool BWD>
-__global__ void __launch_bounds__(256, (HEAD <= 4 && MID <= 12) ? (BWD ? STP_HIER_MINB_BWD : STP_HIER_MINB_FWD) : 1)
+__global__ void __launch_bounds__(256, (HEAD <= 4 && MID <= 12) ? (BWD ? STP_HIER_MINB_BWD : (CULL ? STP_HIER_MINB_FWD_CULL : STP_HIER_MINB_FWD)) : 1)
 render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Sh = HierShared<MID>;
@@ -195,7 +198,9 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     if constexpr (BWD) {
         if (ab.blend_rec != nullptr) active = inside && ab.n_contrib[pix_id] > (uint32_t)ab.rec_cap;
     }
-    int nrec = 0;  // forward: blends of this pixel so far (= position in its blend log)
+    // forward: next slot of this pixel in its blend log (element index into blend_rec, +256 per blend; the host only
+    // enables the log when the whole array can be indexed with 32 bits)
+    uint32_t rec_idx = (uint32_t)tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)tid;
 
     // head queue: sorted by depth, hd[0] is the next to blend
     float hd[HEAD], hs[HEAD];
@@ -225,9 +230,10 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             ps.C2 = ffma(fmul(__ldg(colors + 3 * id + 2), alpha), ps.T, ps.C2);
             ps.T = test_T;
             if (a.blend_rec != nullptr) {
-                if (nrec < a.rec_cap)
-                    a.blend_rec[((size_t)tile_lin * a.rec_cap + nrec) * 256 + tid] = make_uint2((uint32_t)id, __float_as_uint(alpha));
-                ++nrec;
+                // streaming store: the log is written once and read by the backward pass much later
+                const uint32_t rec_end = ((uint32_t)tile_lin + 1u) * (uint32_t)a.rec_cap * 256u;
+                if (rec_idx < rec_end) __stcs(a.blend_rec + rec_idx, make_uint2((uint32_t)id, __float_as_uint(alpha)));
+                rec_idx += 256u;
             }
         } else {
             const float G = hs[0];
@@ -629,8 +635,9 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             a.out_color[plane + pix_id] = ffma(ps.T, f.background[1], ps.C1);
             a.out_color[2 * plane + pix_id] = ffma(ps.T, f.background[2], ps.C2);
             if (a.blend_rec != nullptr) {
-                a.n_contrib[pix_id] = (uint32_t)nrec;
-                if (nrec > a.rec_cap) atomicOr(a.tile_flags + tile_lin, 1u);
+                const uint32_t nrec = (rec_idx - ((uint32_t)tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)tid)) >> 8;
+                a.n_contrib[pix_id] = nrec;
+                if (nrec > (uint32_t)a.rec_cap) atomicOr(a.tile_flags + tile_lin, 1u);
             }
         }
     }
@@ -663,10 +670,10 @@ render_hier_replay_bwd_kernel(Frame f, RenderBwdArgs a) {
     const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
     const uint2* __restrict__ rec = a.blend_rec + (size_t)tile_lin * a.rec_cap * 256 + tid;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    uint2 nxt = rec[0];
+    uint2 nxt = __ldcs(rec);
     for (uint32_t k = 0; k < n; ++k) {
         const uint2 cur = nxt;
-        if (k + 1 < n) nxt = rec[(size_t)(k + 1) * 256];
+        if (k + 1 < n) nxt = __ldcs(rec + (size_t)(k + 1) * 256);
         const int id = (int)cur.x;
         const float alpha = __uint_as_float(cur.y);
         const float4 co = __ldg(a.conic_opacity + id);
