@@ -50,17 +50,36 @@ WORKLOADS = {
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  Uses NVML
+    in-process (nvidia_ml_py) from a background thread: a query costs tens of microseconds, whereas an `nvidia-smi -lms`
+    child process was measured to stall kernel launches for tens of milliseconds per poll (visible as a 30-45 % longer
+    step on the 1.8 ms C2 step).  Falls back to nvidia-smi if NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc, self.first = index, [], None, 0
+        self.index, self.rows, self.proc, self.first, self.stop_flag, self.nvml = index, [], None, 0, False, None
 
     def mark(self):
         self.first = len(self.rows)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -75,19 +94,39 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append([str(sm), str(self.max_sm), "0"] + ["Active" if (r & b) else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is not None:
+            time.sleep(0.03)
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], None, set()
         for r in self.rows[self.first:]:
             try:
@@ -100,7 +139,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def algorithmic_bytes(P, V, R, N, T, M, s_flag, c_flag):

@@ -139,20 +139,37 @@ def _f32(t, device):
 
 
 class _Arena:
-    """one resizable byte buffer handed to the library as an allocation callback
+    """one resizable byte buffer handed to the library through the allocation callback
     (resizeFunctional, rasterize_points.cu:33-41)."""
+    __slots__ = ("device", "tensor", "key")
 
     def __init__(self, device):
         self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.cb = ALLOC_FN(self._alloc)
+        self.tensor = None
+        self.key = id(self)
+        _arenas[self.key] = self
 
-    def _alloc(self, _user, nbytes):
-        try:
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            return self.tensor.data_ptr()
-        except Exception:  # out of memory -> NULL, reported by the library as STP_ERR_ALLOC
-            return None
+    def take(self):
+        """the allocated buffer (an empty tensor if the library never asked); unregisters the arena"""
+        _arenas.pop(self.key, None)
+        if self.tensor is None:
+            self.tensor = torch.empty(0, dtype=torch.uint8, device=self.device)
+        return self.tensor
+
+
+_arenas = {}
+
+
+def _alloc(user, nbytes):
+    arena = _arenas.get(user)
+    try:
+        arena.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=arena.device)
+        return arena.tensor.data_ptr()
+    except Exception:  # out of memory -> NULL, reported by the library as STP_ERR_ALLOC
+        return None
+
+
+_ALLOC_CB = ALLOC_FN(_alloc)  # one C thunk for every call; the arena is identified by the `user` pointer
 
 
 def _stream(device):
@@ -171,12 +188,16 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         raise RuntimeError("render_depth (debug visualisation) is outside the B200 hot path; see DESIGN.md")
     device = means3D.device
     P, H, W = means3D.size(0), int(image_height), int(image_width)
-    out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
-    radii = torch.zeros((P,), dtype=torch.int32, device=device)
-    geom, binning, img = _Arena(device), _Arena(device), _Arena(device)
     st = settings_from_dict(settings_dict, BLEND_RECORD_CAP if record_blends else 0)
-    if P == 0:
-        return 0, out_color, radii, geom.tensor, binning.tensor, img.tensor
+    if P == 0:  # rasterize_points.cu:93
+        e8 = torch.empty(0, dtype=torch.uint8, device=device)
+        return (0, torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device),
+                torch.zeros((0,), dtype=torch.int32, device=device), e8, e8.clone(), e8.clone())
+    # every pixel of the image (of the band, with tile_band) and every radius is written by the kernels
+    alloc = torch.zeros if tile_band is not None else torch.empty
+    out_color = alloc((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    geom, binning, img = _Arena(device), _Arena(device), _Arena(device)
     means3D = _f32(means3D, device)
     keep = [_f32(t, device) for t in (background, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix,
                                       projmatrix, inv_viewprojmatrix, sh, campos)]
@@ -184,17 +205,19 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     M = sh.size(1) if sh is not None and sh.size(0) != 0 else 0
     band = ctypes.byref(StpTileBand(int(tile_band[0]), int(tile_band[1]))) if tile_band is not None else None
     n = ctypes.c_int(0)
-    with torch.cuda.device(device):
-        rc = _lib.stp_forward(geom.cb, None, binning.cb, None, img.cb, None, P, int(degree), M, _ptr(background), W, H,
-                              ctypes.byref(st), band, _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity),
-                              _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
-                              _ptr(viewmatrix), _ptr(projmatrix), _ptr(inv_viewprojmatrix), _ptr(campos),
-                              float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), out_color.data_ptr(),
-                              radii.data_ptr(), int(debug) if not isinstance(debug, bool) else int(debug),
-                              _stream(device), ctypes.byref(n))
+    try:
+        with torch.cuda.device(device):
+            rc = _lib.stp_forward(_ALLOC_CB, geom.key, _ALLOC_CB, binning.key, _ALLOC_CB, img.key, P, int(degree), M,
+                                  _ptr(background), W, H, ctypes.byref(st), band, _ptr(means3D), _ptr(sh), _ptr(colors),
+                                  _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                                  _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(inv_viewprojmatrix),
+                                  _ptr(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
+                                  out_color.data_ptr(), radii.data_ptr(), int(debug), _stream(device), ctypes.byref(n))
+    finally:
+        gt, bt, it = geom.take(), binning.take(), img.take()
     if rc != 0:
         raise RuntimeError(_err())
-    return n.value, out_color, radii, geom.tensor, binning.tensor, img.tensor
+    return n.value, out_color, radii, gt, bt, it
 
 
 def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, scales, rotations, scale_modifier,
