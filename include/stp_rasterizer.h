@@ -58,7 +58,7 @@ typedef struct StpSettings {
     int32_t hierarchical_4x4_culling;
     int32_t load_balancing;   /* scheduling hint only: results never depend on it */
     int32_t proper_ewa_scaling;
-    /* not part of the reference's settings: HIER mode only, blend records per pixel kept by the forward pass for the
+    /* not part of the reference's settings: GLOBAL / HIER modes, blend records per pixel kept by the forward pass for the
      * backward pass (8 B each, in the image arena; stp_image_bytes).  0 = none: backward repeats the re-sort.
      * Must have the same value in stp_forward and the matching stp_backward. */
     int32_t blend_record_cap;

@@ -62,7 +62,8 @@ bool convert_settings(const StpSettings* in, Settings& s, std::string& err, bool
     s.tile_based_culling = in->tile_based_culling != 0;
     s.hier_culling = in->hierarchical_4x4_culling != 0;
     s.proper_ewa_scaling = in->proper_ewa_scaling != 0;
-    s.rec_cap = (in->sort_mode == STP_SORT_HIER && in->blend_record_cap > 0) ? in->blend_record_cap : 0;
+    s.rec_cap = ((in->sort_mode == STP_SORT_HIER || in->sort_mode == STP_SORT_GLOBAL) && in->blend_record_cap > 0)
+                    ? in->blend_record_cap : 0;
     if (s.sort_mode == STP_SORT_HIER) {
         // instantiated queue sizes, forward.cu:445-480 / backward.cu:739-767
         if (s.q_mid != 8 && s.q_mid != 12 && s.q_mid != 20) {
@@ -348,6 +349,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     ra.n_contrib = img.n_contrib;
     ra.out_color = out_color;
     ra.blend_rec = img.blend_rec;
+    ra.blend_count = img.blend_count;
     ra.tile_flags = img.tile_flags;
     ra.rec_cap = s.rec_cap;
     if (s.sort_mode == STP_SORT_GLOBAL) {
@@ -408,6 +410,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     ra.dL_dpix = dL_dpix;
     ra.grad_accum = grad_accum;
     ra.blend_rec = img.blend_rec;
+    ra.blend_count = img.blend_count;
     ra.tile_flags = img.tile_flags;
     ra.rec_cap = s.rec_cap;
     if (R > 0) {
@@ -419,7 +422,7 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
             STP_CUDA(launch_render_hier_bwd(f, s, ra, stream), "render backward (HIER)");
         }
     }
-    g_launches += (R > 0) * ((s.sort_mode == STP_SORT_HIER && s.rec_cap > 0) ? 2 : 1);
+    g_launches += (R > 0) * (s.rec_cap > 0 ? 2 : 1);
     timer.mark("RenderBackward");
 
     PreprocessBwdArgs pa;

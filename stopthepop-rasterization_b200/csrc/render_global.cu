@@ -61,6 +61,7 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
     __shared__ float4 s_co[kBlock];
     __shared__ float s_rgb[3][kBlock];
     __shared__ uint32_t s_mask[kBlock];
+    __shared__ uint32_t s_id[kBlock];  // only used when the blend log is written
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
@@ -70,9 +71,15 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
     const float pxf = (float)px, pyf = (float)py;
     const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
 
-    const uint2 range = a.ranges[tile_y * f.grid_x + tile_x];
+    const uint32_t tile_lin = (uint32_t)(tile_y * f.grid_x + tile_x);
+    const uint2 range = a.ranges[tile_lin];
     int todo = (int)(range.y - range.x);
     const int rounds = (todo + kBlock - 1) / kBlock;
+    // blend log (training steps): slot of this pixel's next blend, blend_rec[tile][k][thread]; 32-bit index (checked by the host)
+    const bool logging = a.blend_rec != nullptr;
+    const uint32_t rec_first = tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)tid;
+    const uint32_t rec_end = (tile_lin + 1u) * (uint32_t)a.rec_cap * 256u;
+    uint32_t rec_idx = rec_first;
 
     bool done = !inside;
     float T = 1.0f;
@@ -92,6 +99,7 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
             s_rgb[0][tid] = a.colors[3 * id + 0];
             s_rgb[1][tid] = a.colors[3 * id + 1];
             s_rgb[2][tid] = a.colors[3 * id + 2];
+            if (logging) s_id[tid] = id;
             mask = strip_mask(xy, co, tile_x0, tile_y0);
         }
         s_mask[tid] = mask;
@@ -121,6 +129,10 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
                 C2 = ffma(T, fmul(alpha, s_rgb[2][j]), C2);
                 T = test_T;
                 last_contributor = (uint32_t)(r * kBlock + j + 1);
+                if (logging) {
+                    if (rec_idx < rec_end) __stcs(a.blend_rec + rec_idx, make_uint2(s_id[j], __float_as_uint(alpha)));
+                    rec_idx += 256u;
+                }
             }
         }
     }
@@ -132,6 +144,11 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
         a.out_color[pix_id] = ffma(T, f.background[0], C0);
         a.out_color[plane + pix_id] = ffma(T, f.background[1], C1);
         a.out_color[2 * plane + pix_id] = ffma(T, f.background[2], C2);
+        if (logging) {
+            const uint32_t nrec = (rec_idx - rec_first) >> 8;
+            a.blend_count[pix_id] = nrec;
+            if (nrec > (uint32_t)a.rec_cap) atomicOr(a.tile_flags + tile_lin, 1u);
+        }
     }
 }
 
@@ -194,6 +211,10 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
     const uint32_t pix_id = (uint32_t)f.W * py + px;
     const float pxf = (float)px, pyf = (float)py;
     const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
+
+    // with a blend log the replay kernel has done every tile whose pixels all fit the log; this list-driven sweep
+    // only handles the tiles that overflowed
+    if (a.blend_rec != nullptr && a.tile_flags[tile_y * f.grid_x + tile_x] == 0u) return;
 
     const uint2 range = a.ranges[tile_y * f.grid_x + tile_x];
     int todo = (int)(range.y - range.x);
@@ -323,6 +344,10 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
 cudaError_t launch_render_global_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream) {
     dim3 grid(f.grid_x, f.row1 - f.row0, 1);
     if (grid.y == 0) return cudaSuccess;
+    if (a.blend_rec != nullptr) {
+        cudaError_t e = cudaMemsetAsync(a.tile_flags, 0, sizeof(uint32_t) * (size_t)f.grid_x * f.grid_y, stream);
+        if (e != cudaSuccess) return e;
+    }
     render_global_fwd_kernel<<<grid, kBlock, 0, stream>>>(f, a);
     return cudaGetLastError();
 }
@@ -330,6 +355,10 @@ cudaError_t launch_render_global_fwd(const Frame& f, const RenderArgs& a, cudaSt
 cudaError_t launch_render_global_bwd(const Frame& f, const RenderBwdArgs& a, cudaStream_t stream) {
     dim3 grid(f.grid_x, f.row1 - f.row0, 1);
     if (grid.y == 0) return cudaSuccess;
+    if (a.blend_rec != nullptr) {
+        cudaError_t e = launch_blend_replay_bwd(f, a, false, true, stream);
+        if (e != cudaSuccess) return e;
+    }
     render_global_bwd_kernel<<<grid, kBlock, 0, stream>>>(f, a);
     return cudaGetLastError();
 }

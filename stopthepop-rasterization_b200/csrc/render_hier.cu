@@ -196,7 +196,7 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
     bool active = inside;
     if constexpr (BWD) {
-        if (ab.blend_rec != nullptr) active = inside && ab.n_contrib[pix_id] > (uint32_t)ab.rec_cap;
+        if (ab.blend_rec != nullptr) active = inside && ab.blend_count[pix_id] > (uint32_t)ab.rec_cap;
     }
     // forward: next slot of this pixel in its blend log (element index into blend_rec, +256 per blend; the host only
     // enables the log when the whole array can be indexed with 32 bits)
@@ -636,27 +636,38 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             a.out_color[2 * plane + pix_id] = ffma(ps.T, f.background[2], ps.C2);
             if (a.blend_rec != nullptr) {
                 const uint32_t nrec = (rec_idx - ((uint32_t)tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)tid)) >> 8;
-                a.n_contrib[pix_id] = nrec;
+                a.blend_count[pix_id] = nrec;
                 if (nrec > (uint32_t)a.rec_cap) atomicOr(a.tile_flags + tile_lin, 1u);
             }
         }
     }
 }
 
-// ---- backward by replay: every pixel walks its own blend log (front to back, like the reference's hierarchical backward
-// :1071-1170) and accumulates the gradients of the logged Gaussians.  Same arithmetic as the BWD branch of blend_one
+// ---- backward by replay (GLOBAL and HIER): every pixel walks its own blend log (front to back, the formulation of the
+// reference's hierarchical / k-buffer backward, hierarchical_render.cuh:1071-1170, resorted_render.cuh:303) and
+// accumulates the gradients of the logged Gaussians.  Same arithmetic as the BWD branch of blend_one
 // above; G is recovered from the logged alpha (alpha / opacity; re-evaluated with expf when alpha was clamped to 0.99).
+template <bool HIER_MAP, bool TILE_FALLBACK>
 __global__ void __launch_bounds__(256)
-render_hier_replay_bwd_kernel(Frame f, RenderBwdArgs a) {
+blend_replay_bwd_kernel(Frame f, RenderBwdArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = lane >> 4, hl = lane & 15;
-    const int b = warp * 2 + half, q = hl >> 2, p = hl & 3;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
-    const int cx = tile_x * 16 + (b & 3) * 4, cy = tile_y * 16 + (b >> 2) * 4;
-    const int px = cx + (q & 1) * 2 + (p & 1), py = cy + (q >> 1) * 2 + (p >> 1);
+    int px, py;
+    if constexpr (HIER_MAP) {  // thread -> pixel map of render_hier_kernel
+        const int half = lane >> 4, hl = lane & 15;
+        const int b = warp * 2 + half, q = hl >> 2, p = hl & 3;
+        px = tile_x * 16 + (b & 3) * 4 + (q & 1) * 2 + (p & 1);
+        py = tile_y * 16 + (b >> 2) * 4 + (q >> 1) * 2 + (p >> 1);
+    } else {                   // ... of render_global_fwd_kernel
+        px = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
+        py = tile_y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    }
     if (px >= f.W || py >= f.H) return;
+    if constexpr (TILE_FALLBACK) {
+        if (a.tile_flags[tile_y * f.grid_x + tile_x] != 0u) return;  // the list-driven kernel does this whole tile
+    }
     const uint32_t pix_id = (uint32_t)f.W * py + px;
-    const uint32_t n = a.n_contrib[pix_id];
+    const uint32_t n = a.blend_count[pix_id];
     if (n == 0u || n > (uint32_t)a.rec_cap) return;
     const float pxf = (float)px, pyf = (float)py;
     const size_t plane = (size_t)f.W * f.H;
@@ -748,13 +759,24 @@ cudaError_t launch_render_hier_fwd(const Frame& f, const Settings& s, const Rend
     return dispatch<false>(f, s, a, dummy, stream);
 }
 
+cudaError_t launch_blend_replay_bwd(const Frame& f, const RenderBwdArgs& a, bool hier_mapping, bool whole_tile_fallback,
+                                    cudaStream_t stream) {
+    dim3 grid(f.grid_x, f.row1 - f.row0, 1);
+    if (grid.y == 0) return cudaSuccess;
+    if (hier_mapping) {
+        if (whole_tile_fallback) blend_replay_bwd_kernel<true, true><<<grid, 256, 0, stream>>>(f, a);
+        else blend_replay_bwd_kernel<true, false><<<grid, 256, 0, stream>>>(f, a);
+    } else {
+        if (whole_tile_fallback) blend_replay_bwd_kernel<false, true><<<grid, 256, 0, stream>>>(f, a);
+        else blend_replay_bwd_kernel<false, false><<<grid, 256, 0, stream>>>(f, a);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_render_hier_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream) {
     RenderArgs dummy{};
     if (a.blend_rec != nullptr) {
-        dim3 grid(f.grid_x, f.row1 - f.row0, 1);
-        if (grid.y == 0) return cudaSuccess;
-        render_hier_replay_bwd_kernel<<<grid, 256, 0, stream>>>(f, a);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = launch_blend_replay_bwd(f, a, true, false, stream);
         if (e != cudaSuccess) return e;
     }
     return dispatch<true>(f, s, dummy, a, stream);  // re-sorting backward: everything, or only the pixels whose log overflowed

@@ -30,7 +30,8 @@ struct RenderArgs {
     float* final_T;
     uint32_t* n_contrib;
     float* out_color;
-    uint2* blend_rec;      // HIER blend log (nullptr = do not record)
+    uint2* blend_rec;      // blend log (nullptr = do not record)
+    uint32_t* blend_count;
     uint32_t* tile_flags;
     int rec_cap;
 };
@@ -47,7 +48,8 @@ struct RenderBwdArgs {
     const float* pixel_colors;
     const float* dL_dpix;
     float* grad_accum;   // [P,12] packed screen-space gradient accumulator (kGradAccum*, zero-filled by the caller)
-    const uint2* blend_rec;  // HIER blend log written by the forward pass (nullptr = re-sort everything)
+    const uint2* blend_rec;  // blend log written by the forward pass (nullptr = list-driven backward for everything)
+    const uint32_t* blend_count;
     const uint32_t* tile_flags;
     int rec_cap;
 };
@@ -114,6 +116,11 @@ cudaError_t launch_render_global_bwd(const Frame& f, const RenderBwdArgs& a, cud
 // render_hier.cu
 cudaError_t launch_render_hier_fwd(const Frame& f, const Settings& s, const RenderArgs& a, cudaStream_t stream);
 cudaError_t launch_render_hier_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream);
+
+// blend-log replay backward (render_hier.cu): hier_mapping selects the thread -> pixel map of the kernel that wrote the
+// log; whole_tile_fallback = skip every pixel of a flagged tile (GLOBAL) instead of only the overflowed pixels (HIER)
+cudaError_t launch_blend_replay_bwd(const Frame& f, const RenderBwdArgs& a, bool hier_mapping, bool whole_tile_fallback,
+                                    cudaStream_t stream);
 
 // render_ppx.cu
 cudaError_t launch_render_kbuffer_fwd(const Frame& f, const Settings& s, const RenderArgs& a, cudaStream_t stream);

@@ -62,10 +62,11 @@ struct ImageState {
     uint32_t* tile_count;
     uint32_t* tile_cursor;
     uint32_t* large_tiles;
-    // HIER blend records (render_hier.cu): the forward pass logs every blend of every pixel, (Gaussian id, alpha), at
-    // [tile][k][thread]; the backward pass replays the log instead of repeating the hierarchical re-sort.  n_contrib
-    // holds the number of blends per pixel (the reference leaves it unwritten in HIER mode); pixels with more than
-    // rec_cap blends set tile_flags and are handled by the re-sorting backward kernel.
+    // Blend log (GLOBAL and HIER training steps): the forward pass logs every blend of every pixel, (Gaussian id, alpha),
+    // at blend_rec[tile][k][thread] and the number of blends in blend_count; the backward pass replays the log front to
+    // back instead of sweeping the tile list again (GLOBAL) / repeating the hierarchical re-sort (HIER).  Pixels with
+    // more than rec_cap blends set tile_flags and are handled by the list-driven backward kernels.
+    uint32_t* blend_count;
     uint32_t* tile_flags;
     uint2* blend_rec;  // nullptr when rec_cap == 0
     int rec_cap;
@@ -78,6 +79,7 @@ struct ImageState {
         obtain(chunk, s.tile_cursor, tiles);
         obtain(chunk, s.large_tiles, tiles);
         obtain(chunk, s.tile_flags, tiles);
+        obtain(chunk, s.blend_count, N);
         s.blend_rec = nullptr;
         s.rec_cap = rec_cap;
         if (rec_cap > 0) obtain(chunk, s.blend_rec, tiles * 256 * (size_t)rec_cap);
@@ -129,7 +131,7 @@ struct Settings {
     int sort_mode, sort_order;
     int q_mid, q_head;
     bool rect_bounding, tight_opacity_bounding, tile_based_culling, hier_culling, proper_ewa_scaling;
-    int rec_cap;  // blend records per pixel (HIER, 0 = none)
+    int rec_cap;  // blend records per pixel (GLOBAL / HIER, 0 = none)
     bool per_tile_depth() const { return sort_order == 2 || sort_order == 3; }
     bool requires_inv() const { return sort_mode != 0 || per_tile_depth(); }
 };

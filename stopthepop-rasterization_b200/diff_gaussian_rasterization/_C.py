@@ -104,9 +104,13 @@ def _err():
     return _lib.stp_last_error().decode("utf-8", "replace")
 
 
-# HIER mode: blends logged per pixel by a forward pass that will be followed by a backward pass (8 B each; the image
-# arena grows by 2 KB per pixel at the default).  Pixels that blend more fall back to the re-sorting backward kernel.
+# Blend log: blends recorded per pixel by a forward pass that will be followed by a backward pass (8 B each; the image
+# arena grows by 2 KB per pixel at the default).  Pixels that blend more fall back to the list-driven backward kernels.
+# HIER: on by default (backward 4.7x faster at C3b: no second hierarchical re-sort).  GLOBAL: implemented and tested but
+# off by default -- measured slower on B200 (C2: fwd 0.35->0.47 ms, bwd 0.96->1.06 ms), because the list-driven GLOBAL
+# backward already pre-reduces every Gaussian's gradient across the warp before touching memory.
 BLEND_RECORD_CAP = int(os.environ.get("STP_BLEND_RECORD_CAP", "256"))
+BLEND_RECORD_MODES = (0, 3) if os.environ.get("STP_BLEND_RECORD_GLOBAL", "0") == "1" else (3,)
 
 
 def settings_from_dict(d, blend_record_cap=0):
@@ -118,7 +122,7 @@ def settings_from_dict(d, blend_record_cap=0):
                        int(q["per_pixel"]), int(bool(cs["rect_bounding"])), int(bool(cs["tight_opacity_bounding"])),
                        int(bool(cs["tile_based_culling"])), int(bool(cs["hierarchical_4x4_culling"])),
                        int(bool(d["load_balancing"])), int(bool(d["proper_ewa_scaling"])),
-                       int(blend_record_cap) if int(ss["sort_mode"]) == 3 else 0)
+                       int(blend_record_cap) if int(ss["sort_mode"]) in BLEND_RECORD_MODES else 0)
 
 
 def _ptr(t):
@@ -180,8 +184,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                         viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
                         degree, campos, prefiltered, settings_dict, render_depth, debug, tile_band=None,
                         record_blends=True):
-    """record_blends (HIER mode only): keep the per-pixel blend log that lets the backward pass skip the hierarchical
-    re-sort; pass False for inference-only calls (GaussianRasterizer does, when no input requires a gradient)."""
+    """record_blends (GLOBAL / HIER modes): keep the per-pixel blend log that lets the backward pass replay the blends
+    instead of sweeping the tile lists again / repeating the hierarchical re-sort; pass False for inference-only calls (GaussianRasterizer does, when no input requires a gradient)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:68-71
     if render_depth:
