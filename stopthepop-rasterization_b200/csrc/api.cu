@@ -62,7 +62,7 @@ bool convert_settings(const StpSettings* in, Settings& s, std::string& err, bool
     s.tile_based_culling = in->tile_based_culling != 0;
     s.hier_culling = in->hierarchical_4x4_culling != 0;
     s.proper_ewa_scaling = in->proper_ewa_scaling != 0;
-    s.rec_cap = ((in->sort_mode == STP_SORT_HIER || in->sort_mode == STP_SORT_GLOBAL) && in->blend_record_cap > 0)
+    s.rec_cap = (in->sort_mode != STP_SORT_PPX_KBUFFER && in->blend_record_cap > 0)
                     ? in->blend_record_cap : 0;
     if (s.sort_mode == STP_SORT_HIER) {
         // instantiated queue sizes, forward.cu:445-480 / backward.cu:739-767
@@ -351,6 +351,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     ra.blend_rec = img.blend_rec;
     ra.blend_count = img.blend_count;
     ra.tile_flags = img.tile_flags;
+    ra.log_overflow = g.counters + 4;
     ra.rec_cap = s.rec_cap;
     if (s.sort_mode == STP_SORT_GLOBAL) {
         STP_CUDA(launch_render_global_fwd(f, ra, stream), "render (GLOBAL)");
@@ -381,8 +382,8 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     std::string err;
     if (!convert_settings(settings, s, err, true)) return fail(STP_ERR_UNSUPPORTED, err);
     if (P <= 0) return STP_OK;  // rasterize_points.cu:191
-    if (s.sort_mode == STP_SORT_PPX_FULL)
-        return fail(STP_ERR_UNSUPPORTED, "Backward not supported for full per-pixel sort");  // backward.cu:735
+    if (s.sort_mode == STP_SORT_PPX_FULL && s.rec_cap == 0)  // backward.cu:735; with the blend log of the forward pass
+        return fail(STP_ERR_UNSUPPORTED, "Backward not supported for full per-pixel sort");  // it is supported (replay)
     if (!geom_buffer || !binning_buffer || !image_buffer) return fail(STP_ERR_INVALID_ARGUMENT, "null arena");
 
     Frame f = make_frame(background, width, height, band, viewmatrix, projmatrix, inv_viewprojmatrix, cam_pos, tan_fovx,
@@ -418,6 +419,17 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
             STP_CUDA(launch_render_global_bwd(f, ra, stream), "render backward (GLOBAL)");
         } else if (s.sort_mode == STP_SORT_PPX_KBUFFER) {
             STP_CUDA(launch_render_kbuffer_bwd(f, s, ra, stream), "render backward (PPX_KBUFFER)");
+        } else if (s.sort_mode == STP_SORT_PPX_FULL) {
+            // no list-driven fallback exists for this mode: a pixel that blended more than the log holds is an error
+            uint32_t overflowed = 0;
+            cudaError_t e = cudaMemcpyAsync(&overflowed, g.counters + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) return cuda_fail(e, "blend log overflow read-back");
+            if (overflowed != 0)
+                return fail(STP_ERR_UNSUPPORTED, "PPX_FULL backward: " + std::to_string(overflowed) +
+                                                     " pixels blended more than blend_record_cap entries; raise "
+                                                     "STP_BLEND_RECORD_CAP");
+            STP_CUDA(launch_render_full_bwd(f, ra, stream), "render backward (PPX_FULL)");
         } else {
             STP_CUDA(launch_render_hier_bwd(f, s, ra, stream), "render backward (HIER)");
         }

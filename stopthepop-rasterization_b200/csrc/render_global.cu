@@ -55,6 +55,7 @@ __device__ __forceinline__ uint32_t strip_mask(float2 xy, float4 co, float tile_
     return mask;
 }
 
+template <bool LOG>  // LOG: write the blend log (off by default for GLOBAL; the plain instantiation carries none of its code)
 __global__ void __launch_bounds__(kBlock)
 render_global_fwd_kernel(Frame f, RenderArgs a) {
     __shared__ float2 s_xy[kBlock];
@@ -76,7 +77,7 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
     int todo = (int)(range.y - range.x);
     const int rounds = (todo + kBlock - 1) / kBlock;
     // blend log (training steps): slot of this pixel's next blend, blend_rec[tile][k][thread]; 32-bit index (checked by the host)
-    const bool logging = a.blend_rec != nullptr;
+    constexpr bool logging = LOG;
     const uint32_t rec_first = tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)tid;
     const uint32_t rec_end = (tile_lin + 1u) * (uint32_t)a.rec_cap * 256u;
     uint32_t rec_idx = rec_first;
@@ -99,7 +100,7 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
             s_rgb[0][tid] = a.colors[3 * id + 0];
             s_rgb[1][tid] = a.colors[3 * id + 1];
             s_rgb[2][tid] = a.colors[3 * id + 2];
-            if (logging) s_id[tid] = id;
+            if constexpr (logging) s_id[tid] = id;
             mask = strip_mask(xy, co, tile_x0, tile_y0);
         }
         s_mask[tid] = mask;
@@ -129,7 +130,7 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
                 C2 = ffma(T, fmul(alpha, s_rgb[2][j]), C2);
                 T = test_T;
                 last_contributor = (uint32_t)(r * kBlock + j + 1);
-                if (logging) {
+                if constexpr (logging) {
                     if (rec_idx < rec_end) __stcs(a.blend_rec + rec_idx, make_uint2(s_id[j], __float_as_uint(alpha)));
                     rec_idx += 256u;
                 }
@@ -144,7 +145,7 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
         a.out_color[pix_id] = ffma(T, f.background[0], C0);
         a.out_color[plane + pix_id] = ffma(T, f.background[1], C1);
         a.out_color[2 * plane + pix_id] = ffma(T, f.background[2], C2);
-        if (logging) {
+        if constexpr (logging) {
             const uint32_t nrec = (rec_idx - rec_first) >> 8;
             a.blend_count[pix_id] = nrec;
             if (nrec > (uint32_t)a.rec_cap) atomicOr(a.tile_flags + tile_lin, 1u);
@@ -348,7 +349,8 @@ cudaError_t launch_render_global_fwd(const Frame& f, const RenderArgs& a, cudaSt
         cudaError_t e = cudaMemsetAsync(a.tile_flags, 0, sizeof(uint32_t) * (size_t)f.grid_x * f.grid_y, stream);
         if (e != cudaSuccess) return e;
     }
-    render_global_fwd_kernel<<<grid, kBlock, 0, stream>>>(f, a);
+    if (a.blend_rec != nullptr) render_global_fwd_kernel<true><<<grid, kBlock, 0, stream>>>(f, a);
+    else render_global_fwd_kernel<false><<<grid, kBlock, 0, stream>>>(f, a);
     return cudaGetLastError();
 }
 
@@ -356,7 +358,7 @@ cudaError_t launch_render_global_bwd(const Frame& f, const RenderBwdArgs& a, cud
     dim3 grid(f.grid_x, f.row1 - f.row0, 1);
     if (grid.y == 0) return cudaSuccess;
     if (a.blend_rec != nullptr) {
-        cudaError_t e = launch_blend_replay_bwd(f, a, false, true, stream);
+        cudaError_t e = launch_blend_replay_bwd(f, a, 0, true, stream);
         if (e != cudaSuccess) return e;
     }
     render_global_bwd_kernel<<<grid, kBlock, 0, stream>>>(f, a);

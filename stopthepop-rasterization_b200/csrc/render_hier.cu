@@ -647,13 +647,16 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
 // reference's hierarchical / k-buffer backward, hierarchical_render.cuh:1071-1170, resorted_render.cuh:303) and
 // accumulates the gradients of the logged Gaussians.  Same arithmetic as the BWD branch of blend_one
 // above; G is recovered from the logged alpha (alpha / opacity; re-evaluated with expf when alpha was clamped to 0.99).
-template <bool HIER_MAP, bool TILE_FALLBACK>
+template <int PIXEL_MAP, bool TILE_FALLBACK>
 __global__ void __launch_bounds__(256)
 blend_replay_bwd_kernel(Frame f, RenderBwdArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
     int px, py;
-    if constexpr (HIER_MAP) {  // thread -> pixel map of render_hier_kernel
+    if constexpr (PIXEL_MAP == 2) {  // row-major inside the tile (render_full_kernel)
+        px = tile_x * 16 + (tid & 15);
+        py = tile_y * 16 + (tid >> 4);
+    } else if constexpr (PIXEL_MAP == 1) {  // thread -> pixel map of render_hier_kernel
         const int half = lane >> 4, hl = lane & 15;
         const int b = warp * 2 + half, q = hl >> 2, p = hl & 3;
         px = tile_x * 16 + (b & 3) * 4 + (q & 1) * 2 + (p & 1);
@@ -759,16 +762,18 @@ cudaError_t launch_render_hier_fwd(const Frame& f, const Settings& s, const Rend
     return dispatch<false>(f, s, a, dummy, stream);
 }
 
-cudaError_t launch_blend_replay_bwd(const Frame& f, const RenderBwdArgs& a, bool hier_mapping, bool whole_tile_fallback,
+cudaError_t launch_blend_replay_bwd(const Frame& f, const RenderBwdArgs& a, int pixel_map, bool whole_tile_fallback,
                                     cudaStream_t stream) {
     dim3 grid(f.grid_x, f.row1 - f.row0, 1);
     if (grid.y == 0) return cudaSuccess;
-    if (hier_mapping) {
-        if (whole_tile_fallback) blend_replay_bwd_kernel<true, true><<<grid, 256, 0, stream>>>(f, a);
-        else blend_replay_bwd_kernel<true, false><<<grid, 256, 0, stream>>>(f, a);
+    if (pixel_map == 1) {
+        if (whole_tile_fallback) blend_replay_bwd_kernel<1, true><<<grid, 256, 0, stream>>>(f, a);
+        else blend_replay_bwd_kernel<1, false><<<grid, 256, 0, stream>>>(f, a);
+    } else if (pixel_map == 0) {
+        if (whole_tile_fallback) blend_replay_bwd_kernel<0, true><<<grid, 256, 0, stream>>>(f, a);
+        else blend_replay_bwd_kernel<0, false><<<grid, 256, 0, stream>>>(f, a);
     } else {
-        if (whole_tile_fallback) blend_replay_bwd_kernel<false, true><<<grid, 256, 0, stream>>>(f, a);
-        else blend_replay_bwd_kernel<false, false><<<grid, 256, 0, stream>>>(f, a);
+        blend_replay_bwd_kernel<2, false><<<grid, 256, 0, stream>>>(f, a);
     }
     return cudaGetLastError();
 }
@@ -776,7 +781,7 @@ cudaError_t launch_blend_replay_bwd(const Frame& f, const RenderBwdArgs& a, bool
 cudaError_t launch_render_hier_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream) {
     RenderArgs dummy{};
     if (a.blend_rec != nullptr) {
-        cudaError_t e = launch_blend_replay_bwd(f, a, true, false, stream);
+        cudaError_t e = launch_blend_replay_bwd(f, a, 1, false, stream);
         if (e != cudaSuccess) return e;
     }
     return dispatch<true>(f, s, dummy, a, stream);  // re-sorting backward: everything, or only the pixels whose log overflowed

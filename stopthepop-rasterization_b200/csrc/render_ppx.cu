@@ -278,6 +278,8 @@ render_full_kernel(Frame f, RenderArgs a) {
     const int n = (int)(range.y - range.x);
     const int rounds = (n + 255) / 256;
 
+    const bool logging = a.blend_rec != nullptr;
+    const uint32_t tile_lin = (uint32_t)(tile_y * f.grid_x + tile_x);
     // warp w renders the 32 pixels of rows 2w, 2w+1 of the tile, one after the other
     for (int pi = 0; pi < 32; ++pi) {
         const uint32_t px = tile_x * 16 + (pi & 15), py = tile_y * 16 + warp * 2 + (pi >> 4);
@@ -314,6 +316,9 @@ render_full_kernel(Frame f, RenderArgs a) {
         uint32_t last_contributor = 0;
         bool done = false;
         int todo = n;
+        // blend log of this pixel (row-major position warp*32+pi inside the tile): blend_rec[tile][k][position]
+        const uint32_t rec_first = tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)(warp * 32 + pi);
+        uint32_t nrec = 0;
         for (int rd = 0; rd < rounds && !done; ++rd, todo -= 256) {
 #pragma unroll
             for (int r = 24; r < 32; ++r) {  // the round's 256 new entries take item 0 of every thread (:588-600)
@@ -331,8 +336,10 @@ render_full_kernel(Frame f, RenderArgs a) {
                     const int e = r * 32 + lane;
                     float alpha = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
                     bool accept = false;
+                    int my_id = -1;
                     if (e < lim && v[r] >= 0) {
                         const int id = (int)__ldg(a.point_list + range.x + (v[r] >> 10));
+                        my_id = id;
                         const float2 xy = __ldg(a.means2D + id);
                         const float4 co = __ldg(a.conic_opacity + id);
                         const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
@@ -364,6 +371,11 @@ render_full_kernel(Frame f, RenderArgs a) {
                         C2 = ffma(fmul(b2, al), T, C2);
                         T = test_T;
                         last_contributor = (uint32_t)(rd * 256 + r * 32 + l + 1);
+                        if (logging) {
+                            if (lane == l && nrec < (uint32_t)a.rec_cap)
+                                __stcs(a.blend_rec + rec_first + nrec * 256u, make_uint2((uint32_t)my_id, __float_as_uint(al)));
+                            ++nrec;
+                        }
                     }
                     if ((r + 1) * 32 >= lim) stop = true;
                 }
@@ -382,6 +394,10 @@ render_full_kernel(Frame f, RenderArgs a) {
             a.out_color[pix_id] = ffma(T, f.background[0], C0);
             a.out_color[plane + pix_id] = ffma(T, f.background[1], C1);
             a.out_color[2 * plane + pix_id] = ffma(T, f.background[2], C2);
+            if (logging) {
+                a.blend_count[pix_id] = nrec;
+                if (nrec > (uint32_t)a.rec_cap) atomicAdd(a.log_overflow, 1u);
+            }
         }
     }
 }
@@ -419,6 +435,12 @@ cudaError_t launch_render_full_fwd(const Frame& f, const RenderArgs& a, cudaStre
     if (grid.y == 0) return cudaSuccess;
     render_full_kernel<<<grid, kBlock, 0, stream>>>(f, a);
     return cudaGetLastError();
+}
+
+// PPX_FULL backward: the reference has none (backward.cu:733-736).  With the blend log of the forward pass it is the
+// same replay as for the other modes: the per-pixel sort order is held fixed, like in the k-buffer / hierarchical backward.
+cudaError_t launch_render_full_bwd(const Frame& f, const RenderBwdArgs& a, cudaStream_t stream) {
+    return launch_blend_replay_bwd(f, a, 2, false, stream);
 }
 
 }  // namespace stp

@@ -33,6 +33,7 @@ struct RenderArgs {
     uint2* blend_rec;      // blend log (nullptr = do not record)
     uint32_t* blend_count;
     uint32_t* tile_flags;
+    uint32_t* log_overflow;  // counter: pixels whose log overflowed in a mode without list-driven backward (PPX_FULL)
     int rec_cap;
 };
 
@@ -117,15 +118,16 @@ cudaError_t launch_render_global_bwd(const Frame& f, const RenderBwdArgs& a, cud
 cudaError_t launch_render_hier_fwd(const Frame& f, const Settings& s, const RenderArgs& a, cudaStream_t stream);
 cudaError_t launch_render_hier_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream);
 
-// blend-log replay backward (render_hier.cu): hier_mapping selects the thread -> pixel map of the kernel that wrote the
-// log; whole_tile_fallback = skip every pixel of a flagged tile (GLOBAL) instead of only the overflowed pixels (HIER)
-cudaError_t launch_blend_replay_bwd(const Frame& f, const RenderBwdArgs& a, bool hier_mapping, bool whole_tile_fallback,
+// blend-log replay backward (render_hier.cu): pixel_map selects the thread -> pixel map of the kernel that wrote the
+// log (0 GLOBAL strips, 1 HIER blocks/quads, 2 row-major = PPX_FULL); whole_tile_fallback = skip every pixel of a flagged tile (GLOBAL) instead of only the overflowed pixels (HIER)
+cudaError_t launch_blend_replay_bwd(const Frame& f, const RenderBwdArgs& a, int pixel_map, bool whole_tile_fallback,
                                     cudaStream_t stream);
 
 // render_ppx.cu
 cudaError_t launch_render_kbuffer_fwd(const Frame& f, const Settings& s, const RenderArgs& a, cudaStream_t stream);
 cudaError_t launch_render_kbuffer_bwd(const Frame& f, const Settings& s, const RenderBwdArgs& a, cudaStream_t stream);
 cudaError_t launch_render_full_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream);
+cudaError_t launch_render_full_bwd(const Frame& f, const RenderBwdArgs& a, cudaStream_t stream);
 
 // preprocess_bwd.cu
 cudaError_t launch_preprocess_bwd(const PreprocessBwdArgs& a, const Frame& f, cudaStream_t stream);

@@ -34,7 +34,8 @@ struct GeometryState {
     float4* conic_opacity;
     float* rgb;
     uint32_t* tiles_touched;
-    uint32_t* counters;  // [1] R (total instances), [2] error flags, [3] number of tiles on the large-tile sort list
+    uint32_t* counters;  // [1] R (total instances), [2] error flags, [3] number of tiles on the large-tile sort list,
+                         // [4] pixels whose blend log overflowed in PPX_FULL mode
 
     static GeometryState from_chunk(char*& chunk, size_t P, bool inv) {
         GeometryState g;

@@ -110,7 +110,8 @@ def _err():
 # off by default -- measured slower on B200 (C2: fwd 0.35->0.47 ms, bwd 0.96->1.06 ms), because the list-driven GLOBAL
 # backward already pre-reduces every Gaussian's gradient across the warp before touching memory.
 BLEND_RECORD_CAP = int(os.environ.get("STP_BLEND_RECORD_CAP", "256"))
-BLEND_RECORD_MODES = (0, 3) if os.environ.get("STP_BLEND_RECORD_GLOBAL", "0") == "1" else (3,)
+# PPX_FULL: on -- the log is what makes a backward pass possible at all (the reference has none, backward.cu:733-736).
+BLEND_RECORD_MODES = (0, 1, 3) if os.environ.get("STP_BLEND_RECORD_GLOBAL", "0") == "1" else (1, 3)
 
 
 def settings_from_dict(d, blend_record_cap=0):

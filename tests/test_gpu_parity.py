@@ -28,7 +28,7 @@ def run_ours(f, backward=True, band=None, settings=None, record_cap=None):
     from diff_gaussian_rasterization import _C
     dev = _dev()
     if record_cap is not None:  # blend-log capacity (default: _C.BLEND_RECORD_CAP), log enabled for GLOBAL as well
-        saved, _C.BLEND_RECORD_CAP, _C.BLEND_RECORD_MODES = (_C.BLEND_RECORD_CAP, _C.BLEND_RECORD_MODES), record_cap, (0, 3)
+        saved, _C.BLEND_RECORD_CAP, _C.BLEND_RECORD_MODES = (_C.BLEND_RECORD_CAP, _C.BLEND_RECORD_MODES), record_cap, (0, 1, 3)
         try:
             return run_ours(f, backward, band, settings)
         finally:
@@ -122,10 +122,57 @@ def test_backward_replay_and_list_driven_agree(golden, name, cap):
         assert rel <= TOL, (k, rel)
 
 
-def test_full_sort_backward_raises(golden):
+def test_full_sort_backward_raises_without_blend_log(golden):
     f = golden("full_sort")
     with pytest.raises(RuntimeError, match="Backward not supported for full per-pixel sort"):  # backward.cu:733-736
-        run_ours(f, backward=True)
+        run_ours(f, backward=True, record_cap=0)
+
+
+@pytest.mark.parametrize("P,seed,sigma", [(1500, 12, 0.5), (3000, 13, 0.4)])
+def test_full_sort_backward_by_replay(P, seed, sigma):
+    """PPX_FULL backward does not exist in the reference (backward.cu:733-736); here the blend log of the forward pass
+    makes it a replay.  Derived pin of SURVEY 8c(i): on scenes where every pixel has at most 24 surviving candidates
+    (checked with the CPU oracle when the scenes were chosen: FULL and KBUFFER(24) forward images are identical) the
+    k-buffer backward IS the backward of an exact per-pixel sort, so FULL-by-replay must give its gradients -- ours and,
+    when oracle/_ref is present, the reference build's."""
+    from diff_gaussian_rasterization import _C
+    from oracle import ref_api as ref
+    import stp_scenes as S
+    dev = _dev()
+    W, H = 64, 48
+    sc, cam = S.make_scene(P, W, H, seed, sigma_scale=sigma)
+    sc, cam = S.to_device(sc, dev), S.to_device(cam, dev)
+    dL = S.make_upstream_grad(W, H, 3000 + seed).to(dev)
+    e = torch.empty(0, device=dev)
+
+    def both(d):
+        out = _C.rasterize_gaussians(cam.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e, cam.viewmatrix,
+                                     cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx, cam.tanfovy, H, W, sc.shs, 3,
+                                     cam.campos, False, d, False, False)
+        g = _C.rasterize_gaussians_backward(cam.bg, sc.means3D, out[2], sc.opacities, e, sc.scales, sc.rotations, 1.0, e,
+                                            cam.viewmatrix, cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx,
+                                            cam.tanfovy, out[1], dL, sc.shs, 3, cam.campos, out[3], out[0], out[4], out[5],
+                                            d, False)
+        return out, g
+    d_full, d_kb = S.default_settings_dict(sort_mode=1), S.default_settings_dict(sort_mode=2, per_pixel=24)
+    (of, gf), (ok, gk) = both(d_full), both(d_kb)
+    assert (of[1] - ok[1]).abs().max().item() <= 1e-6
+    for a, b in zip(gf, gk):
+        m = b.abs().max().item()
+        assert (a - b).abs().max().item() <= TOL * max(m, 1e-30)
+    if ref.available():
+        rr = ref.forward(sc, cam, d_kb)
+        rg, rg2 = ref.backward(sc, cam, d_kb, rr, dL), ref.backward(sc, cam, d_kb, rr, dL)
+        for a, b, b2 in zip(gf, rg, rg2):
+            m = b.abs().max().item()
+            noise = (b - b2).abs().max().item() / max(m, 1e-30)
+            assert (a - b).abs().max().item() <= max(TOL, 10 * noise) * max(m, 1e-30)
+
+
+def test_full_sort_backward_reports_log_overflow(golden):
+    f = golden("full_sort")
+    with pytest.raises(RuntimeError, match="raise STP_BLEND_RECORD_CAP"):
+        run_ours(f, backward=True, record_cap=2)
 
 
 @pytest.mark.parametrize("name", ["global_default", "hier_preset", "kbuffer16", "full_sort"])
