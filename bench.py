@@ -46,7 +46,12 @@ WORKLOADS = {
     "C2": ("C2", dict(), "C2: 1M Gaussians, 1920x1080, GLOBAL tile sort, fwd+bwd (BASELINE.json configs[1])"),
     "C3a": ("C3", dict(sort_mode=3), "C3a: 4M Gaussians, 1920x1080, HIER 64/8/4, fwd+bwd"),
     "C3b": ("C3", dict(S.STOPTHEPOP_PRESET), "C3b: 4M Gaussians, 1920x1080, StopThePop preset, fwd+bwd"),
+    # BASELINE.json configs[3]: one 4K view, full per-pixel sort, screen tiles sharded across the ranks (tile-row bands)
+    "C4": ("C4", dict(sort_mode=1), "C4: 4M Gaussians, 3840x2160, PPX_FULL, fwd+bwd, tile-row bands sharded across ranks"),
+    # BASELINE.json configs[4]: 10M Gaussians, one 1080p view per rank (8 views at 8 GPUs), StopThePop preset
+    "C5": ("C5", dict(S.STOPTHEPOP_PRESET), "C5: 10M Gaussians, one 1920x1080 view per rank, StopThePop preset, fwd+bwd"),
 }
+BAND_SHARDED = {"C4"}  # strong scaling: all ranks render ONE frame; everything else: one view per rank (weak scaling)
 
 
 class ClockSampler:
@@ -225,6 +230,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--points", type=int, default=0, help="override the number of Gaussians of the workload's scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace-steps", action="store_true", help="diagnostics: per-step times of every timed region")
     a = ap.parse_args()
@@ -238,7 +244,11 @@ def main():
     scene_name, overrides, desc = WORKLOADS[a.workload]
     settings = S.default_settings_dict(**overrides)
     cid, P, W, H = S.CONFIGS[scene_name]
+    if a.points:
+        P = a.points
+        desc += f" [--points {P}]"
     pixels = W * H
+    bands_mode = a.workload in BAND_SHARDED
 
     from oracle import ref_api as ref
     use_ref_gpu = a.impl == "reference" and ref.available() and torch.cuda.is_available()
@@ -247,7 +257,7 @@ def main():
         # no reference CUDA build travelled with the repo: the C oracle port on the host cores
         if rank != 0:
             return
-        sc_c, cam_c = S.make_config(scene_name)
+        sc_c, cam_c = S.make_config(scene_name, P=P)
         dL_c = S.make_upstream_grad(W, H, 2000 + cid)
         for _ in range(1):
             cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, 1)
@@ -269,9 +279,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- workload: same Gaussians on every rank, one camera per rank ---------------------------------------
-    sc_c, cam0_c = S.make_config(scene_name)
-    cam_c, _, _ = S.make_camera(W, H, yaw=0.08 * rank)
-    dL_c = S.make_upstream_grad(W, H, 2000 + cid + rank)
+    sc_c, cam0_c = S.make_config(scene_name, P=P)
+    cam_c, _, _ = S.make_camera(W, H, yaw=0.0 if bands_mode else 0.08 * rank)
+    dL_c = S.make_upstream_grad(W, H, 2000 + cid + (0 if bands_mode else rank))
+    import stp_sharding as SH
+    grid_y = (H + 15) // 16
+    bands = SH.equal_bands(grid_y, world) if bands_mode else None
+    my_band = bands[rank] if bands_mode and world > 1 else None
     sc, cam = S.to_device(sc_c, dev), S.to_device(cam_c, dev)
     dL = dL_c.to(dev)
     e = torch.empty(0, device=dev)
@@ -283,13 +297,14 @@ def main():
         def fwd(c, dbg=2):
             return _C.rasterize_gaussians(c.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e,
                                           c.viewmatrix, c.projmatrix, c.inv_viewprojmatrix, c.tanfovx, c.tanfovy, H, W,
-                                          sc.shs, sc.sh_degree, c.campos, False, settings, False, dbg)
+                                          sc.shs, sc.sh_degree, c.campos, False, settings, False, dbg, tile_band=my_band)
 
         def bwd(c, out, g, dbg=2):
             return _C.rasterize_gaussians_backward(c.bg, sc.means3D, out[2], sc.opacities, e, sc.scales, sc.rotations,
                                                    1.0, e, c.viewmatrix, c.projmatrix, c.inv_viewprojmatrix, c.tanfovx,
                                                    c.tanfovy, out[1], g, sc.shs, sc.sh_degree, c.campos, out[3], out[0],
-                                                   out[4], out[5], settings, dbg, want_param_slab=True)
+                                                   out[4], out[5], settings, dbg, want_param_slab=True,
+                                                   tile_band=my_band)
     else:
         def fwd(c, dbg=False):
             return ref.forward(sc, c, settings)
@@ -300,8 +315,15 @@ def main():
 
     state = {}
 
+    full_sort_ref = a.impl == "reference" and settings["sort_settings"]["sort_mode"] == 1  # the reference has no backward
+
     def step_resident():
         out = fwd(cam)
+        if bands_mode and world > 1 and a.impl == "ours":
+            state["image"] = SH.gather_image_bands(out[1], bands)  # the ONE forward exchange of tile sharding
+        if full_sort_ref:
+            state["out"] = out
+            return
         grads, slab = bwd(cam, out, dL)
         if world > 1:
             if a.impl == "ours":
@@ -340,17 +362,23 @@ def main():
         if a.impl == "ours":
             rs = GaussianRasterizationSettings(H, W, cam_c.tanfovx, cam_c.tanfovy, bg, 1.0, vm, pm, iv, sc.sh_degree, cp,
                                                False, ext_settings, False, False)
-            color, radii = GaussianRasterizer(rs)(m3, means2D, op, shs=sh, scales=scl, rotations=rot)
+            color, radii = GaussianRasterizer(rs, tile_band=my_band)(m3, means2D, op, shs=sh, scales=scl, rotations=rot)
+            if bands_mode and world > 1:
+                color_full = SH.gather_image_bands(color.detach(), bands)
         else:
             c = cam._replace(viewmatrix=vm, projmatrix=pm, inv_viewprojmatrix=iv, campos=cp, bg=bg)
             out = ref.forward(sc, c, settings)
             color = out[1]
+        img_out = color_full if (a.impl == "ours" and bands_mode and world > 1) else color.detach()
         ev_f.record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_f)
-            h_img.copy_(color.detach(), non_blocking=True)
-        color.record_stream(copy_stream)
+            h_img.copy_(img_out, non_blocking=True)
+        img_out.record_stream(copy_stream)
         main.wait_event(ev_g)
+        if full_sort_ref:
+            main.wait_stream(copy_stream)
+            return
         if a.impl == "ours":
             color.backward(g_dev)
             if world > 1:
@@ -406,10 +434,11 @@ def main():
         stages = _C.timing_summary()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / a.steps
-    value = world * pixels / (ms_step * 1e-3) / 1e6
+    views = 1 if bands_mode else world  # tile sharding: all ranks render ONE frame (strong scaling)
+    value = views * pixels / (ms_step * 1e-3) / 1e6
 
     ms_e2e = event_time_ms(step_e2e, a.steps, a.warmup, world) / a.steps
-    e2e_value = world * pixels / (ms_e2e * 1e-3) / 1e6
+    e2e_value = views * pixels / (ms_e2e * 1e-3) / 1e6
     e2e_full = None
     if a.impl == "ours" and world == 1:
         ms_full = event_time_ms(step_e2e_full, max(3, a.steps // 4), 3, world) / max(3, a.steps // 4)
@@ -426,10 +455,13 @@ def main():
     V = int((out[2] > 0).sum().item())
     line = {
         "metric": "Mpixels/s fwd+bwd", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if bands_mode else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "P": P, "W": W, "H": H, "visible": V, "num_rendered": R,
-                   "sharding": "views (one camera per rank, replicated Gaussians, NCCL all-reduce of parameter grads)"
+                   "sharding": ("tile-row bands of one view (replicated Gaussians, NCCL all-gather of the image bands + "
+                                "all-reduce of parameter grads)" if bands_mode else
+                                "views (one camera per rank, replicated Gaussians, NCCL all-reduce of parameter grads)")
                    if world > 1 else "single GPU",
                    "l2_policy": "inputs larger than L2 (236 B/Gaussian x P + instance lists >> 126 MB)" if P >= 10**6
                    else "small parity config; L2-resident"},
@@ -440,6 +472,9 @@ def main():
                         "streams are done); Gaussian parameters (model state) resident"},
         "clocks": clocks,
     }
+    if full_sort_ref:
+        line["config"]["note"] = ("reference arm is FORWARD ONLY: the reference has no PPX_FULL backward "
+                                  "(backward.cu:733-736); ours is forward + backward")
     if a.impl == "ours":
         N, T = pixels, ((W + 15) // 16) * ((H + 15) // 16)
         s_flag = 0 if settings["sort_settings"]["sort_mode"] == 0 else 1
@@ -471,7 +506,7 @@ def main():
         line["gpu_launches"] = int(launches)
         if e2e_full:
             line["e2e_full_upload"] = e2e_full
-        if world == 1 and not a.no_cpu_baseline:
+        if world == 1 and not a.no_cpu_baseline and settings["sort_settings"]["sort_mode"] != 1:
             reps = 2 if P <= 10**6 else 1
             sc_b, cam_b, dL_b, sample = sc_c, cam_c, dL_c, f"{reps} full step(s) of the workload"
             if P > 10**6:  # bound the CPU work: same camera, first 1M Gaussians of the cloud

@@ -362,7 +362,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     } else {
         STP_CUDA(launch_render_hier_fwd(f, s, ra, stream), "render (HIER)");
     }
-    g_launches += 1;
+    g_launches += (s.sort_mode == STP_SORT_PPX_FULL) ? 2 : 1;
     timer.mark("Render");
     timer.finish();
     return STP_OK;

@@ -18,6 +18,7 @@
 //      capacity are chunk-sorted and merged through a global ping-pong buffer (merge path).
 // HBM traffic: 8 B written + 8 B read + 12 B written per instance.
 #include "stp_kernels.cuh"
+#include "stp_sort.cuh"
 
 namespace stp {
 
@@ -210,31 +211,6 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ count, uint2* __restric
 // Every warp keeps a span of 32*E consecutive elements in registers (lane L holds elements L, L+32, ... of the span):
 // compare-exchange distances below 32 are warp shuffles, distances 32 .. 16*E are register-to-register, and only
 // distances of a whole span or more go through shared memory -- for a 512-entry tile 6 of the 45 stages.
-template <int E>
-__device__ __forceinline__ void reg_stage(uint64_t (&v)[E], int j, int k, int base, int lane) {
-    if (j >= 32) {
-        const int jj = j >> 5;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if ((e & jj) == 0) {
-                const bool up = ((base + e * 32 + lane) & k) == 0;
-                const uint64_t a = v[e], b = v[e | jj];
-                const bool sw = (a > b) == up;
-                v[e] = sw ? b : a;
-                v[e | jj] = sw ? a : b;
-            }
-        }
-    } else {
-        const bool lower = (lane & j) == 0;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const bool up = ((base + e * 32 + lane) & k) == 0;
-            const uint64_t o = __shfl_xor_sync(0xffffffffu, v[e], j);
-            v[e] = ((v[e] < o) == (lower == up)) ? v[e] : o;
-        }
-    }
-}
-
 // sorts src[0,n) and hands element i of the sorted sequence to emit(i, value).  s: np * 8 bytes of shared memory.
 template <int E, int THREADS, typename Emit>
 __device__ __forceinline__ void bitonic_sort_tile(const uint64_t* src, int n, int np, uint64_t* __restrict__ s, int tid,

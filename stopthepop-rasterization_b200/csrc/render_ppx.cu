@@ -17,6 +17,7 @@
 // starts from the first 1024), sorts, emits the 256 smallest in order, keeps the rest.  The sort is exact
 // for lists <= 1024 entries, like the reference.
 #include "stp_kernels.cuh"
+#include "stp_sort.cuh"
 
 namespace stp {
 
@@ -268,6 +269,196 @@ __device__ __forceinline__ void bitonic_sort_1024(float (&k)[32], int (&v)[32], 
     }
 }
 
+// ---- fast path for tiles of at most 1024 instances ------------------------------------------------------------------
+// For such a tile the reference's sliding window holds the whole list from the first round on, i.e. the blending
+// order is the exact sort of ALL entries by the pixel's ray depth -- and entries that fail the alpha test never
+// blend.  So it is enough to sort the SURVIVORS of the alpha test (typically a tenth of the list): same image,
+// same final_T, and n_contrib (= rank of the last contributor among all entries + 1) follows from one counting pass
+// over the keys.  Exact key ties, whose order in the reference depends on the history of its window, are not
+// resolved here: a pixel with a tie among its survivors, a tie of its last contributor with any entry, or more
+// than kFastSurv survivors is marked (n_contrib = ~0) and left to render_full_kernel below.
+constexpr int kFastSurv = 256;
+constexpr uint32_t kSlowMark = 0xFFFFFFFFu;
+struct FullFastShared {
+    uint32_t key[8][1024];                 // order-preserving integer image of every entry's ray depth, per warp
+    unsigned long long surv[8][kFastSurv]; // (key << 32 | slot) of the alpha-test survivors
+    float alpha[8][kFastSurv];
+    int id[8][kFastSurv];
+};
+
+__device__ __forceinline__ uint32_t sortable_bits(float x) {  // monotone float -> uint32 (-0 folded into +0)
+    const uint32_t b = __float_as_uint(x + 0.0f);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+// sorts the S survivors of one pixel (E*32 >= S) and blends them front to back; returns false if a key tie was found
+template <int E>
+__device__ __forceinline__ bool full_fast_sort_blend(const FullFastShared& sh, int warp, int lane, int S, const RenderArgs& a,
+                                                     bool logging, uint32_t rec_first, float& T, float& C0, float& C1,
+                                                     float& C2, uint32_t& last_key, bool& have_last, uint32_t& nrec) {
+    uint64_t v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int e = r * 32 + lane;
+        v[r] = e < S ? sh.surv[warp][e] : ~0ull;
+    }
+#pragma unroll
+    for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) reg_stage<E>(v, j, k, 0, lane);
+    }
+    // key ties among neighbours of the sorted sequence?
+    bool tie = false;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const uint32_t mine = (uint32_t)(v[r] >> 32);
+        uint32_t next = __shfl_down_sync(0xffffffffu, mine, 1);
+        const uint32_t wrap = __shfl_sync(0xffffffffu, (uint32_t)(v[(r + 1 < E) ? r + 1 : r] >> 32), 0);
+        if (lane == 31) next = (r + 1 < E) ? wrap : 0xFFFFFFFFu;
+        tie |= (r * 32 + lane + 1 < S) && mine == next;
+    }
+    if (__any_sync(0xffffffffu, tie)) return false;
+    bool done = false;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        if (done || r * 32 >= S) break;
+        const int e = r * 32 + lane;
+        const bool valid = e < S;
+        const uint32_t slot = (uint32_t)v[r] & (kFastSurv - 1);
+        const uint32_t mykey = (uint32_t)(v[r] >> 32);
+        float alpha = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        int id = -1;
+        if (valid) {
+            alpha = sh.alpha[warp][slot];
+            id = sh.id[warp][slot];
+            c0 = __ldg(a.colors + 3 * id + 0);
+            c1 = __ldg(a.colors + 3 * id + 1);
+            c2 = __ldg(a.colors + 3 * id + 2);
+        }
+        const int cnt = min(32, S - r * 32);
+        for (int l = 0; l < cnt; ++l) {
+            const float al = __shfl_sync(0xffffffffu, alpha, l);
+            const float test_T = fmul(T, fsub(1.0f, al));
+            if (test_T < kTThreshold) {
+                done = true;
+                break;
+            }
+            const float b0 = __shfl_sync(0xffffffffu, c0, l), b1 = __shfl_sync(0xffffffffu, c1, l),
+                        b2 = __shfl_sync(0xffffffffu, c2, l);
+            C0 = ffma(fmul(b0, al), T, C0);
+            C1 = ffma(fmul(b1, al), T, C1);
+            C2 = ffma(fmul(b2, al), T, C2);
+            T = test_T;
+            last_key = __shfl_sync(0xffffffffu, mykey, l);
+            have_last = true;
+            if (logging) {
+                if (lane == l && nrec < (uint32_t)a.rec_cap)
+                    __stcs(a.blend_rec + rec_first + nrec * 256u, make_uint2((uint32_t)id, __float_as_uint(al)));
+                ++nrec;
+            }
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kBlock)
+render_full_fast_kernel(Frame f, RenderArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_full[];
+    FullFastShared& sh = *reinterpret_cast<FullFastShared*>(smem_full);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
+    const size_t plane = (size_t)f.W * f.H;
+    const uint32_t tile_lin = (uint32_t)(tile_y * f.grid_x + tile_x);
+    const uint2 range = a.ranges[tile_lin];
+    const int n = (int)(range.y - range.x);
+    if (n > 1024) return;  // render_full_kernel emulates the sliding window for long lists
+    const RayCam cam = make_raycam(f.inv_viewproj, f.cam_pos, f.W, f.H);
+    const bool logging = a.blend_rec != nullptr;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (int pi = 0; pi < 32; ++pi) {
+        const uint32_t px = tile_x * 16 + (pi & 15), py = tile_y * 16 + warp * 2 + (pi >> 4);
+        if (!(px < (uint32_t)f.W && py < (uint32_t)f.H)) continue;  // warp-uniform
+        const uint32_t pix_id = (uint32_t)f.W * py + px;
+        const float pxf = (float)px, pyf = (float)py;
+        const Vec3 ray = view_ray(cam, pxf, pyf);
+        __syncwarp();  // the previous pixel's reads of this warp's shared-memory rows are complete
+        int S = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int idx = base + lane;
+            bool accept = false;
+            uint32_t skey = 0xFFFFFFFFu;
+            float alpha = 0.f;
+            int id = -1;
+            if (idx < n) {
+                id = (int)__ldg(a.point_list + range.x + idx);
+                float ic[6], ux, uy, uz;
+                load_inv(a.cov3D_inv, id, ic, ux, uy, uz);
+                skey = sortable_bits(depth_along_ray(ic, ux, uy, uz, ray));
+                sh.key[warp][idx] = skey;
+                const float2 xy = __ldg(a.means2D + id);
+                const float4 co = __ldg(a.conic_opacity + id);
+                const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
+                const float pw = opacity_factor(dx, dy, co.x, co.y, co.z);
+                if (!(pw < 0.0f)) {
+                    alpha = fminf(0.99f, fmul(co.w, expf(-pw)));
+                    accept = !(alpha < kAlphaThreshold);
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, accept);
+            const int slot = S + __popc(m & lt_mask);
+            if (accept && slot < kFastSurv) {
+                sh.surv[warp][slot] = ((unsigned long long)skey << 32) | (unsigned long long)slot;
+                sh.alpha[warp][slot] = alpha;
+                sh.id[warp][slot] = id;
+            }
+            S += __popc(m);
+        }
+        __syncwarp();
+        float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+        uint32_t last_key = 0, nrec = 0;
+        bool have_last = false;
+        const uint32_t rec_first = tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)(warp * 32 + pi);
+        bool ok = S <= kFastSurv;
+        if (ok) {
+            if (S <= 32) ok = full_fast_sort_blend<1>(sh, warp, lane, S, a, logging, rec_first, T, C0, C1, C2, last_key, have_last, nrec);
+            else if (S <= 64) ok = full_fast_sort_blend<2>(sh, warp, lane, S, a, logging, rec_first, T, C0, C1, C2, last_key, have_last, nrec);
+            else if (S <= 128) ok = full_fast_sort_blend<4>(sh, warp, lane, S, a, logging, rec_first, T, C0, C1, C2, last_key, have_last, nrec);
+            else ok = full_fast_sort_blend<8>(sh, warp, lane, S, a, logging, rec_first, T, C0, C1, C2, last_key, have_last, nrec);
+        }
+        uint32_t last_contributor = 0;
+        if (ok && have_last) {
+            // rank of the last contributor among ALL entries of the tile
+            int less = 0, equal = 0;
+            for (int idx = lane; idx < n; idx += 32) {
+                const uint32_t kk = sh.key[warp][idx];
+                less += kk < last_key;
+                equal += kk == last_key;
+            }
+            less = __reduce_add_sync(0xffffffffu, less);
+            equal = __reduce_add_sync(0xffffffffu, equal);
+            if (equal != 1) ok = false;
+            last_contributor = (uint32_t)less + 1u;
+        }
+        if (lane == 0) {
+            if (!ok) {
+                a.n_contrib[pix_id] = kSlowMark;
+            } else {
+                a.final_T[pix_id] = T;
+                a.n_contrib[pix_id] = last_contributor;
+                a.out_color[pix_id] = ffma(T, f.background[0], C0);
+                a.out_color[plane + pix_id] = ffma(T, f.background[1], C1);
+                a.out_color[2 * plane + pix_id] = ffma(T, f.background[2], C2);
+                if (logging) {
+                    a.blend_count[pix_id] = nrec;
+                    if (nrec > (uint32_t)a.rec_cap) atomicAdd(a.log_overflow, 1u);
+                }
+            }
+        }
+    }
+}
+
+// ---- exact emulation of the reference's sliding window: long lists, and the pixels the fast path gave up on -------------
 __global__ void __launch_bounds__(kBlock)
 render_full_kernel(Frame f, RenderArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -285,6 +476,7 @@ render_full_kernel(Frame f, RenderArgs a) {
         const uint32_t px = tile_x * 16 + (pi & 15), py = tile_y * 16 + warp * 2 + (pi >> 4);
         if (!(px < (uint32_t)f.W && py < (uint32_t)f.H)) continue;  // warp-uniform
         const uint32_t pix_id = (uint32_t)f.W * py + px;
+        if (n <= 1024 && a.n_contrib[pix_id] != kSlowMark) continue;  // done by render_full_fast_kernel (warp-uniform)
         const float pxf = (float)px, pyf = (float)py;
         const Vec3 ray = view_ray(cam, pxf, pyf);
 
@@ -433,6 +625,12 @@ cudaError_t launch_render_kbuffer_bwd(const Frame& f, const Settings& s, const R
 cudaError_t launch_render_full_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream) {
     dim3 grid(f.grid_x, f.row1 - f.row0, 1);
     if (grid.y == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(render_full_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullFastShared));
+        attr_set = true;
+    }
+    render_full_fast_kernel<<<grid, kBlock, sizeof(FullFastShared), stream>>>(f, a);
     render_full_kernel<<<grid, kBlock, 0, stream>>>(f, a);
     return cudaGetLastError();
 }

@@ -48,6 +48,7 @@ def rasterize_gaussians(
     rotations,
     cov3Ds_precomp,
     raster_settings,
+    tile_band=None,
 ):
     return _RasterizeGaussians.apply(
         means3D,
@@ -59,6 +60,7 @@ def rasterize_gaussians(
         rotations,
         cov3Ds_precomp,
         raster_settings,
+        tile_band,
     )
 
 
@@ -67,7 +69,8 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, tile_band=None):
+        # tile_band (ours only, multi-GPU tile sharding): (row0, row1) of 16-pixel tile rows this rank renders
         rs = raster_settings
         args = (
             rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
@@ -79,16 +82,17 @@ class _RasterizeGaussians(torch.autograd.Function):
             cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
             try:
                 num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(
-                    *args, record_blends=any(ctx.needs_input_grad))
+                    *args, record_blends=any(ctx.needs_input_grad), tile_band=tile_band)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
             num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(
-                *args, record_blends=any(ctx.needs_input_grad))
+                *args, record_blends=any(ctx.needs_input_grad), tile_band=tile_band)
 
         ctx.raster_settings = rs
+        ctx.tile_band = tile_band
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, means3D, opacities, scales, rotations, cov3Ds_precomp, radii, sh, color,
                               geomBuffer, binningBuffer, imgBuffer)
@@ -108,13 +112,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:
-                grads8 = _C.rasterize_gaussians_backward(*args)
+                grads8 = _C.rasterize_gaussians_backward(*args, tile_band=ctx.tile_band)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise ex
         else:
-            grads8 = _C.rasterize_gaussians_backward(*args)
+            grads8 = _C.rasterize_gaussians_backward(*args, tile_band=ctx.tile_band)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
          grad_rotations) = grads8
         return (
@@ -126,6 +130,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_scales,
             grad_rotations,
             grad_cov3Ds_precomp,
+            None,
             None,
         )
 
@@ -254,9 +259,12 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings):
+    def __init__(self, raster_settings, tile_band=None):
+        """tile_band (ours only): (row0, row1) band of 16-pixel tile rows rendered / differentiated by this rank when
+        one view is sharded across GPUs (stp_sharding.py); None = the whole image, as in the reference."""
         super().__init__()
         self.raster_settings = raster_settings
+        self.tile_band = tile_band
 
     def markVisible(self, positions):
         # Mark visible points (based on frustum culling for camera) with a boolean
@@ -289,4 +297,4 @@ class GaussianRasterizer(nn.Module):
 
         # Invoke the CUDA rasterization routine
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                   raster_settings)
+                                   raster_settings, self.tile_band)
