@@ -170,17 +170,31 @@ MIN_WARM_S = 0.4  # the W warm-up steps are extended to at least this long (SM c
 STEP_TRACE = []  # --trace-steps: per-step event times of every timed region (diagnostics, adds one event per step)
 
 
-def event_time_ms(fn, steps, warmup, world, min_warm_s=0.0):
-    """W untimed warm-ups (and at least min_warm_s seconds of them, so that the SM clocks have ramped up from idle
-    before the timed region starts), then exactly K steps bracketed by barrier + synchronize; max over ranks."""
+def warm_up(fn, warmup, world, min_warm_s):
+    """W warm-up steps, extended to at least min_warm_s seconds (the SM clocks ramp up from idle).  The number of extra
+    steps is derived from the all-reduced (max) time of the first W, so every rank runs the SAME number of steps -- a
+    per-rank time-based loop would desynchronise the collectives inside fn."""
     t0 = time.perf_counter()
-    n = 0
-    while n < warmup or time.perf_counter() - t0 < min_warm_s:
+    for _ in range(warmup):
         fn()
-        n += 1
-        if n % 8 == 0:
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    per_step = max(elapsed / max(warmup, 1), 1e-4)
+    extra = 0 if elapsed >= min_warm_s else min(20000, int((min_warm_s - elapsed) / per_step) + 1)
+    for i in range(extra):
+        fn()
+        if (i + 1) % 8 == 0:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
+
+
+def event_time_ms(fn, steps, warmup, world, min_warm_s=0.0):
+    """W untimed warm-ups (see warm_up), then exactly K steps bracketed by barrier + synchronize; max over ranks."""
+    if warmup > 0 or min_warm_s > 0:
+        warm_up(fn, warmup, world, min_warm_s)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -276,7 +290,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     # ---- workload: same Gaussians on every rank, one camera per rank ---------------------------------------
     sc_c, cam0_c = S.make_config(scene_name, P=P)
@@ -414,15 +429,7 @@ def main():
         sampler.start()  # before the warm-up: nvidia-smi's start-up cost stays outside the timed region
     if a.impl == "ours":
         _C.timing_reset()
-        t_w = time.perf_counter()
-        n_w = 0
-        while n_w < a.warmup or time.perf_counter() - t_w < MIN_WARM_S:
-            step_resident()
-            n_w += 1
-            if n_w % 8 == 0:
-                torch.cuda.synchronize()
-                _C.timing_reset()
-        torch.cuda.synchronize()
+        warm_up(step_resident, a.warmup, world, MIN_WARM_S)
         _C.timing_reset()
         launches0 = _C.kernel_launches()
     if rank == 0:
