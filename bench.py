@@ -306,6 +306,8 @@ def main():
     e = torch.empty(0, device=dev)
     M = sc.shs.shape[1]
 
+    # ours: the gradient all-reduce is issued by the library, overlapped with the preprocess-backward stage (_C.py)
+    sync_group = dist.group.WORLD if (world > 1 and a.impl == "ours") else None
     if a.impl == "ours":
         from diff_gaussian_rasterization import (ExtendedSettings, GaussianRasterizationSettings, GaussianRasterizer, _C)
 
@@ -319,7 +321,7 @@ def main():
                                                    1.0, e, c.viewmatrix, c.projmatrix, c.inv_viewprojmatrix, c.tanfovx,
                                                    c.tanfovy, out[1], g, sc.shs, sc.sh_degree, c.campos, out[3], out[0],
                                                    out[4], out[5], settings, dbg, want_param_slab=True,
-                                                   tile_band=my_band)
+                                                   tile_band=my_band, sync_group=sync_group)
     else:
         def fwd(c, dbg=False):
             return ref.forward(sc, c, settings)
@@ -340,12 +342,9 @@ def main():
             state["out"] = out
             return
         grads, slab = bwd(cam, out, dL)
-        if world > 1:
-            if a.impl == "ours":
-                dist.all_reduce(slab)
-            else:
-                for t in (slab[3], slab[5], slab[2], slab[6], slab[7]):
-                    dist.all_reduce(t)
+        if world > 1 and a.impl != "ours":
+            for t in (slab[3], slab[5], slab[2], slab[6], slab[7]):
+                dist.all_reduce(t)
         state["out"], state["grads"] = out, grads
 
     # ---- e2e: public API, per-step host inputs -------------------------------------------------------------
@@ -377,7 +376,8 @@ def main():
         if a.impl == "ours":
             rs = GaussianRasterizationSettings(H, W, cam_c.tanfovx, cam_c.tanfovy, bg, 1.0, vm, pm, iv, sc.sh_degree, cp,
                                                False, ext_settings, False, False)
-            color, radii = GaussianRasterizer(rs, tile_band=my_band)(m3, means2D, op, shs=sh, scales=scl, rotations=rot)
+            color, radii = GaussianRasterizer(rs, tile_band=my_band, sync_group=sync_group)(
+                m3, means2D, op, shs=sh, scales=scl, rotations=rot)
             if bands_mode and world > 1:
                 color_full = SH.gather_image_bands(color.detach(), bands)
         else:
@@ -395,10 +395,7 @@ def main():
             main.wait_stream(copy_stream)
             return
         if a.impl == "ours":
-            color.backward(g_dev)
-            if world > 1:
-                for t in leaves:
-                    dist.all_reduce(t.grad)
+            color.backward(g_dev)  # parameter gradients come back already summed over the ranks (sync_group)
         else:
             grads = ref.backward(sc, c, settings, out, g_dev)
             if world > 1:
@@ -468,7 +465,8 @@ def main():
         "config": {"workload": desc, "P": P, "W": W, "H": H, "visible": V, "num_rendered": R,
                    "sharding": ("tile-row bands of one view (replicated Gaussians, NCCL all-gather of the image bands + "
                                 "all-reduce of parameter grads)" if bands_mode else
-                                "views (one camera per rank, replicated Gaussians, NCCL all-reduce of parameter grads)")
+                                "views (one camera per rank, replicated Gaussians, NCCL all-reduce of parameter grads, "
+                                "overlapped with the preprocess-backward stage)")
                    if world > 1 else "single GPU",
                    "l2_policy": "inputs larger than L2 (236 B/Gaussian x P + instance lists >> 126 MB)" if P >= 10**6
                    else "small parity config; L2-resident"},

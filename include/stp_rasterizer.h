@@ -125,6 +125,40 @@ int stp_backward(int P, int D, int M, int R,
                  float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                  int debug, void* stream);
 
+/* The two halves of stp_backward as separate calls (same argument list), for data-parallel callers that overlap the
+ * gradient exchange with the computation: stp_backward_render runs the render-backward stage (fills grad_accum);
+ * stp_backward_preprocess then produces the dL_* rows of Gaussians [first, first+count) (first % 256 == 0), so the
+ * all-reduce of one row range can run while the next range is computed (diff_gaussian_rasterization/_C.py,
+ * sync_group=...).  stp_backward == stp_backward_render + stp_backward_preprocess(0, P). */
+int stp_backward_render(int P, int D, int M, int R,
+                 const float* background, int width, int height,
+                 const StpSettings* settings, const StpTileBand* band,
+                 const float* means3D, const float* shs, const float* opacities,
+                 const float* colors_precomp, const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp,
+                 const float* viewmatrix, const float* projmatrix, const float* inv_viewprojmatrix,
+                 const float* cam_pos, float tan_fovx, float tan_fovy,
+                 const float* pixel_colors, const int* radii,
+                 char* geom_buffer, char* binning_buffer, char* image_buffer,
+                 const float* dL_dpix,
+                 float* dL_dmean2D, float* grad_accum, float* dL_dopacity, float* dL_dcolor,
+                 float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                 int debug, void* stream);
+int stp_backward_preprocess(int P, int D, int M, int R,
+                 const float* background, int width, int height,
+                 const StpSettings* settings, const StpTileBand* band,
+                 const float* means3D, const float* shs, const float* opacities,
+                 const float* colors_precomp, const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp,
+                 const float* viewmatrix, const float* projmatrix, const float* inv_viewprojmatrix,
+                 const float* cam_pos, float tan_fovx, float tan_fovy,
+                 const float* pixel_colors, const int* radii,
+                 char* geom_buffer, char* binning_buffer, char* image_buffer,
+                 const float* dL_dpix,
+                 float* dL_dmean2D, float* grad_accum, float* dL_dopacity, float* dL_dcolor,
+                 float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                 int debug, void* stream, int first, int count);
+
 /* replaces: CudaRasterizer::Rasterizer::markVisible, rasterizer.h:188-193 (rasterizer_impl.cu:161-173);
  * present is a device array of P bytes (bool). projmatrix is accepted and unused, as in the reference. */
 int stp_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

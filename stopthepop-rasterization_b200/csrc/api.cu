@@ -368,15 +368,19 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     return STP_OK;
 }
 
-int stp_backward(int P, int D, int M, int R, const float* background, int width, int height, const StpSettings* settings,
-                 const StpTileBand* band, const float* means3D, const float* shs, const float* opacities,
-                 const float* colors_precomp, const float* scales, float scale_modifier, const float* rotations,
-                 const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
-                 const float* inv_viewprojmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
-                 const float* pixel_colors, const int* radii, char* geom_buffer, char* binning_buffer,
-                 char* image_buffer, const float* dL_dpix, float* dL_dmean2D, float* grad_accum, float* dL_dopacity,
-                 float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-                 int debug, void* stream_) {
+}  // extern "C"
+
+namespace {
+// which = 1: render backward only; 2: preprocess backward only (Gaussians [first, first+count)); 3: both
+int backward_impl(int which, int first, int count, int P, int D, int M, int R, const float* background, int width,
+                  int height, const StpSettings* settings, const StpTileBand* band, const float* means3D, const float* shs,
+                  const float* opacities, const float* colors_precomp, const float* scales, float scale_modifier,
+                  const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                  const float* inv_viewprojmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                  const float* pixel_colors, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                  const float* dL_dpix, float* dL_dmean2D, float* grad_accum, float* dL_dopacity, float* dL_dcolor,
+                  float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int debug,
+                  void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     Settings s;
     std::string err;
@@ -385,6 +389,8 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     if (s.sort_mode == STP_SORT_PPX_FULL && s.rec_cap == 0)  // backward.cu:735; with the blend log of the forward pass
         return fail(STP_ERR_UNSUPPORTED, "Backward not supported for full per-pixel sort");  // it is supported (replay)
     if (!geom_buffer || !binning_buffer || !image_buffer) return fail(STP_ERR_INVALID_ARGUMENT, "null arena");
+    if ((which & 2) && (first < 0 || (first & 255) != 0 || count < 0 || first + count > P))
+        return fail(STP_ERR_INVALID_ARGUMENT, "preprocess-backward range must start at a multiple of 256 inside [0,P]");
 
     Frame f = make_frame(background, width, height, band, viewmatrix, projmatrix, inv_viewprojmatrix, cam_pos, tan_fovx,
                          tan_fovy);
@@ -398,59 +404,86 @@ int stp_backward(int P, int D, int M, int R, const float* background, int width,
     char* ip = image_buffer;
     ImageState img = ImageState::from_chunk(ip, (size_t)width * height, (size_t)tiles, s.rec_cap);
 
-    RenderBwdArgs ra;
-    ra.ranges = img.ranges;
-    ra.point_list = b.point_list;
-    ra.means2D = g.means2D;
-    ra.conic_opacity = g.conic_opacity;
-    ra.cov3D_inv = g.cov3D_inv;
-    ra.colors = colors_precomp != nullptr ? colors_precomp : g.rgb;
-    ra.final_T = img.final_T;
-    ra.n_contrib = img.n_contrib;
-    ra.pixel_colors = pixel_colors;
-    ra.dL_dpix = dL_dpix;
-    ra.grad_accum = grad_accum;
-    ra.blend_rec = img.blend_rec;
-    ra.blend_count = img.blend_count;
-    ra.tile_flags = img.tile_flags;
-    ra.rec_cap = s.rec_cap;
-    if (R > 0) {
-        if (s.sort_mode == STP_SORT_GLOBAL) {
-            STP_CUDA(launch_render_global_bwd(f, ra, stream), "render backward (GLOBAL)");
-        } else if (s.sort_mode == STP_SORT_PPX_KBUFFER) {
-            STP_CUDA(launch_render_kbuffer_bwd(f, s, ra, stream), "render backward (PPX_KBUFFER)");
-        } else if (s.sort_mode == STP_SORT_PPX_FULL) {
-            // no list-driven fallback exists for this mode: a pixel that blended more than the log holds is an error
-            uint32_t overflowed = 0;
-            cudaError_t e = cudaMemcpyAsync(&overflowed, g.counters + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-            if (e != cudaSuccess) return cuda_fail(e, "blend log overflow read-back");
-            if (overflowed != 0)
-                return fail(STP_ERR_UNSUPPORTED, "PPX_FULL backward: " + std::to_string(overflowed) +
-                                                     " pixels blended more than blend_record_cap entries; raise "
-                                                     "STP_BLEND_RECORD_CAP");
-            STP_CUDA(launch_render_full_bwd(f, ra, stream), "render backward (PPX_FULL)");
-        } else {
-            STP_CUDA(launch_render_hier_bwd(f, s, ra, stream), "render backward (HIER)");
+    if (which & 1) {
+        RenderBwdArgs ra;
+        ra.ranges = img.ranges;
+        ra.point_list = b.point_list;
+        ra.means2D = g.means2D;
+        ra.conic_opacity = g.conic_opacity;
+        ra.cov3D_inv = g.cov3D_inv;
+        ra.colors = colors_precomp != nullptr ? colors_precomp : g.rgb;
+        ra.final_T = img.final_T;
+        ra.n_contrib = img.n_contrib;
+        ra.pixel_colors = pixel_colors;
+        ra.dL_dpix = dL_dpix;
+        ra.grad_accum = grad_accum;
+        ra.blend_rec = img.blend_rec;
+        ra.blend_count = img.blend_count;
+        ra.tile_flags = img.tile_flags;
+        ra.rec_cap = s.rec_cap;
+        if (R > 0) {
+            if (s.sort_mode == STP_SORT_GLOBAL) {
+                STP_CUDA(launch_render_global_bwd(f, ra, stream), "render backward (GLOBAL)");
+            } else if (s.sort_mode == STP_SORT_PPX_KBUFFER) {
+                STP_CUDA(launch_render_kbuffer_bwd(f, s, ra, stream), "render backward (PPX_KBUFFER)");
+            } else if (s.sort_mode == STP_SORT_PPX_FULL) {
+                // no list-driven fallback exists for this mode: a pixel that blended more than the log holds is an error
+                uint32_t overflowed = 0;
+                cudaError_t e = cudaMemcpyAsync(&overflowed, g.counters + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+                if (e != cudaSuccess) return cuda_fail(e, "blend log overflow read-back");
+                if (overflowed != 0)
+                    return fail(STP_ERR_UNSUPPORTED, "PPX_FULL backward: " + std::to_string(overflowed) +
+                                                         " pixels blended more than blend_record_cap entries; raise "
+                                                         "STP_BLEND_RECORD_CAP");
+                STP_CUDA(launch_render_full_bwd(f, ra, stream), "render backward (PPX_FULL)");
+            } else {
+                STP_CUDA(launch_render_hier_bwd(f, s, ra, stream), "render backward (HIER)");
+            }
         }
+        g_launches += (R > 0) * ((s.rec_cap > 0 && s.sort_mode != STP_SORT_PPX_FULL) ? 2 : 1);
+        timer.mark("RenderBackward");
     }
-    g_launches += (R > 0) * (s.rec_cap > 0 ? 2 : 1);
-    timer.mark("RenderBackward");
 
-    PreprocessBwdArgs pa;
-    pa.P = P; pa.D = D; pa.M = M;
-    pa.means3D = means3D; pa.radii = radii; pa.shs = shs; pa.clamped = g.clamped; pa.opacities = opacities;
-    pa.scales = scales; pa.rotations = rotations; pa.scale_modifier = scale_modifier;
-    pa.cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
-    pa.proper_ewa_scaling = s.proper_ewa_scaling;
-    pa.dL_dmean2D = dL_dmean2D; pa.grad_accum = grad_accum; pa.dL_dopacity = dL_dopacity;
-    pa.dL_dmean3D = dL_dmean3D; pa.dL_dcolor = dL_dcolor; pa.dL_dcov3D = dL_dcov3D; pa.dL_dsh = dL_dsh;
-    pa.dL_dscale = dL_dscale; pa.dL_drot = dL_drot;
-    STP_CUDA(launch_preprocess_bwd(pa, f, stream), "preprocess backward");
-    g_launches += 1;
-    timer.mark("PreprocessBackward");
+    if (which & 2) {
+        PreprocessBwdArgs pa;
+        pa.P = P; pa.D = D; pa.M = M;
+        pa.first = first; pa.P_end = first + count;
+        pa.means3D = means3D; pa.radii = radii; pa.shs = shs; pa.clamped = g.clamped; pa.opacities = opacities;
+        pa.scales = scales; pa.rotations = rotations; pa.scale_modifier = scale_modifier;
+        pa.cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
+        pa.proper_ewa_scaling = s.proper_ewa_scaling;
+        pa.dL_dmean2D = dL_dmean2D; pa.grad_accum = grad_accum; pa.dL_dopacity = dL_dopacity;
+        pa.dL_dmean3D = dL_dmean3D; pa.dL_dcolor = dL_dcolor; pa.dL_dcov3D = dL_dcov3D; pa.dL_dsh = dL_dsh;
+        pa.dL_dscale = dL_dscale; pa.dL_drot = dL_drot;
+        STP_CUDA(launch_preprocess_bwd(pa, f, stream), "preprocess backward");
+        g_launches += count > 0;
+        timer.mark("PreprocessBackward");
+    }
     timer.finish();
     return STP_OK;
 }
+}  // namespace
+
+extern "C" {
+
+#define STP_BWD_PARAMS                                                                                                       \
+    int P, int D, int M, int R, const float *background, int width, int height, const StpSettings *settings,                 \
+        const StpTileBand *band, const float *means3D, const float *shs, const float *opacities,                             \
+        const float *colors_precomp, const float *scales, float scale_modifier, const float *rotations,                      \
+        const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, const float *inv_viewprojmatrix,       \
+        const float *cam_pos, float tan_fovx, float tan_fovy, const float *pixel_colors, const int *radii,                   \
+        char *geom_buffer, char *binning_buffer, char *image_buffer, const float *dL_dpix, float *dL_dmean2D,                \
+        float *grad_accum, float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D, float *dL_dcov3D, float *dL_dsh,         \
+        float *dL_dscale, float *dL_drot, int debug, void *stream
+#define STP_BWD_ARGS                                                                                                         \
+    P, D, M, R, background, width, height, settings, band, means3D, shs, opacities, colors_precomp, scales, scale_modifier, \
+        rotations, cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, cam_pos, tan_fovx, tan_fovy, pixel_colors,    \
+        radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dmean2D, grad_accum, dL_dopacity, dL_dcolor,          \
+        dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream
+
+int stp_backward(STP_BWD_PARAMS) { return backward_impl(3, 0, P, STP_BWD_ARGS); }
+int stp_backward_render(STP_BWD_PARAMS) { return backward_impl(1, 0, 0, STP_BWD_ARGS); }
+int stp_backward_preprocess(STP_BWD_PARAMS, int first, int count) { return backward_impl(2, first, count, STP_BWD_ARGS); }
 
 }  // extern "C"

@@ -78,14 +78,16 @@ __device__ __forceinline__ void move_sh_rows(float* __restrict__ gptr, int rows,
 __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
     extern __shared__ float s_rows[];  // [8 warps][32 rows][3M+1]
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    // Gaussians [a.first, a.P_end): the launch can cover a sub-range so that a data-parallel caller can start the
+    // all-reduce of one range of gradient rows while the next range is still being computed (a.first % 256 == 0)
+    const int idx = a.first + blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool valid = idx < a.P;
+    const bool valid = idx < a.P_end;
     const bool alive = valid && a.radii[idx] > 0;
     const uint32_t live = __ballot_sync(0xffffffffu, alive);
     const int n_sh = a.M * 3, sh_stride = n_sh + 1;
-    const int warp_base = blockIdx.x * blockDim.x + warp * 32;
-    const int rows = min(32, a.P - warp_base);
+    const int warp_base = a.first + blockIdx.x * blockDim.x + warp * 32;
+    const int rows = min(32, a.P_end - warp_base);
     const bool has_sh = a.shs != nullptr && n_sh > 0;
     // Every row of every output (dL_dmean2D / dL_dcolor / dL_dopacity included) is written here: culled Gaussians get
     // zeros, so the caller does not have to clear these buffers (the reference memsets 256 B per Gaussian per
@@ -412,7 +414,9 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
 cudaError_t launch_preprocess_bwd(const PreprocessBwdArgs& a, const Frame& f, cudaStream_t stream) {
     const size_t smem = (a.shs != nullptr && a.M > 0) ? sizeof(float) * 8 * 32 * (a.M * 3 + 1) : 0;
     cudaFuncSetAttribute(preprocess_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, smem, stream>>>(a, f);
+    const int count = a.P_end - a.first;
+    if (count <= 0) return cudaSuccess;
+    preprocess_bwd_kernel<<<(count + 255) / 256, 256, smem, stream>>>(a, f);
     return cudaGetLastError();
 }
 

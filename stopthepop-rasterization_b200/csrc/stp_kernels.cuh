@@ -57,6 +57,7 @@ struct RenderBwdArgs {
 
 struct PreprocessBwdArgs {
     int P, D, M;
+    int first, P_end;  // Gaussian range [first, P_end) of this launch (first % 256 == 0)
     const float* means3D;
     const int* radii;
     const float* shs;

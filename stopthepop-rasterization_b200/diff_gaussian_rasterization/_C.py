@@ -94,6 +94,11 @@ _lib.stp_backward.argtypes = [
     _P, _P, _P, _P, _P, _P, _P, _P, _P,  # 9 grads
     ctypes.c_int, _P]
 
+_lib.stp_backward_render.restype = ctypes.c_int
+_lib.stp_backward_render.argtypes = list(_lib.stp_backward.argtypes)
+_lib.stp_backward_preprocess.restype = ctypes.c_int
+_lib.stp_backward_preprocess.argtypes = list(_lib.stp_backward.argtypes) + [ctypes.c_int, ctypes.c_int]
+
 if _lib.stp_abi_version() != 3:
     raise ImportError("libstp_rasterizer.so ABI version mismatch")
 
@@ -228,7 +233,13 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy,
                                  pixel_colors, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                 imageBuffer, settings_dict, debug, tile_band=None, want_param_slab=False):
+                                 imageBuffer, settings_dict, debug, tile_band=None, want_param_slab=False,
+                                 sync_group=None, sync_chunks=4):
+    """sync_group (ours only): a torch.distributed process group over which the five PARAMETER gradients are summed
+    before they are returned (data-parallel training: views or tile bands sharded across GPUs).  The exchange is
+    overlapped with the computation: the preprocess-backward stage runs in `sync_chunks` ranges of Gaussians and the
+    all-reduce of each range's SH-gradient rows (81 % of the bytes) starts on a side stream as soon as the range is
+    done; only the last range and the small arrays remain exposed."""
     device = means3D.device
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)  # rasterize_points.cu:169-170
@@ -239,14 +250,14 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
     # preprocess-backward kernel (zeros for culled Gaussians).  The five PARAMETER gradients come first and
     # contiguous, so a data-parallel caller can all-reduce them as one buffer (stp_sharding.py); the per-view
     # intermediates follow.
-    widths = [3, 3 * M, 3, 4, 1, 3, 3, 6, 12]  # means3D sh scales rot opacity | means2D colors cov3D | accumulator
+    widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 12]  # sh means3D scales rot opacity | means2D colors cov3D | accumulator
     flat = torch.empty((sum(widths) * P,), dtype=torch.float32, device=device)
     flat[sum(widths[:8]) * P:].zero_()
     views, off = [], 0
     for w in widths:
         views.append(flat[off:off + w * P])
         off += w * P
-    dL_dmeans3D, dL_dsh, dL_dscales, dL_drot, dL_dopacity, dL_dmeans2D, dL_dcolors, dL_dcov3D, grad_accum = views
+    dL_dsh, dL_dmeans3D, dL_dscales, dL_drot, dL_dopacity, dL_dmeans2D, dL_dcolors, dL_dcov3D, grad_accum = views
     param_slab = flat[:sum(widths[:5]) * P]
     if P != 0:
         means3D = _f32(means3D, device)
@@ -256,21 +267,57 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
          pixel_colors, dL_dout_color, sh, campos) = keep
         radii = radii.contiguous()
         band = ctypes.byref(StpTileBand(int(tile_band[0]), int(tile_band[1]))) if tile_band is not None else None
+        args = (P, int(degree), M, int(R), _ptr(background), W, H, ctypes.byref(st), band, _ptr(means3D), _ptr(sh),
+                _ptr(opacities), _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                _ptr(viewmatrix), _ptr(projmatrix), _ptr(inv_viewprojmatrix), _ptr(campos), float(tan_fovx),
+                float(tan_fovy), _ptr(pixel_colors), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer),
+                _ptr(imageBuffer), _ptr(dL_dout_color), _ptr(dL_dmeans2D), _ptr(grad_accum), _ptr(dL_dopacity),
+                _ptr(dL_dcolors), _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh) if M else None, _ptr(dL_dscales),
+                _ptr(dL_drot), int(debug), _stream(device))
         with torch.cuda.device(device):
-            rc = _lib.stp_backward(P, int(degree), M, int(R), _ptr(background), W, H, ctypes.byref(st), band,
-                                   _ptr(means3D), _ptr(sh), _ptr(opacities), _ptr(colors), _ptr(scales),
-                                   float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
-                                   _ptr(projmatrix), _ptr(inv_viewprojmatrix), _ptr(campos), float(tan_fovx),
-                                   float(tan_fovy), _ptr(pixel_colors), _ptr(radii), _ptr(geomBuffer),
-                                   _ptr(binningBuffer), _ptr(imageBuffer), _ptr(dL_dout_color), _ptr(dL_dmeans2D),
-                                   _ptr(grad_accum), _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D),
-                                   _ptr(dL_dcov3D), _ptr(dL_dsh) if M else None, _ptr(dL_dscales), _ptr(dL_drot),
-                                   int(debug), _stream(device))
+            if sync_group is None:
+                rc = _lib.stp_backward(*args)
+            else:
+                rc = _backward_overlapped(args, P, M, dL_dsh, flat[3 * M * P:sum(widths[:5]) * P], sync_group,
+                                          int(sync_chunks), device)
         if rc != 0:
             raise RuntimeError(_err())
     grads8 = (dL_dmeans2D.view(P, 3), dL_dcolors.view(P, NUM_CHANNELS), dL_dopacity.view(P, 1), dL_dmeans3D.view(P, 3),
               dL_dcov3D.view(P, 6), dL_dsh.view(P, M, 3), dL_dscales.view(P, 3), dL_drot.view(P, 4))
     return (grads8, param_slab) if want_param_slab else grads8
+
+
+_comm_streams = {}
+
+
+def _backward_overlapped(args, P, M, dL_dsh, small, group, chunks, device):
+    """render backward, then preprocess backward range by range with the all-reduce of each finished range of
+    dL_dsh rows running on a side stream (NCCL enqueues behind the stream that is current when it is called)."""
+    import torch.distributed as dist
+    rc = _lib.stp_backward_render(*args)
+    if rc != 0:
+        return rc
+    main = torch.cuda.current_stream(device)
+    comm = _comm_streams.get(device)
+    if comm is None:
+        comm = _comm_streams[device] = torch.cuda.Stream(device=device)
+    step = max(256, ((P + max(chunks, 1) - 1) // max(chunks, 1) + 255) // 256 * 256)
+    for first in range(0, P, step):
+        count = min(step, P - first)
+        rc = _lib.stp_backward_preprocess(*args, first, count)
+        if rc != 0:
+            return rc
+        ev = torch.cuda.Event()
+        ev.record(main)
+        if M:
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                dist.all_reduce(dL_dsh[first * 3 * M:(first + count) * 3 * M], group=group)
+    with torch.cuda.stream(comm):
+        comm.wait_stream(main)
+        dist.all_reduce(small, group=group)
+    main.wait_stream(comm)
+    return 0
 
 
 def blend_record_cap_of(imageBuffer, W, H):

@@ -49,6 +49,7 @@ def rasterize_gaussians(
     cov3Ds_precomp,
     raster_settings,
     tile_band=None,
+    sync_group=None,
 ):
     return _RasterizeGaussians.apply(
         means3D,
@@ -61,6 +62,7 @@ def rasterize_gaussians(
         cov3Ds_precomp,
         raster_settings,
         tile_band,
+        sync_group,
     )
 
 
@@ -69,8 +71,9 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, tile_band=None):
+                raster_settings, tile_band=None, sync_group=None):
         # tile_band (ours only, multi-GPU tile sharding): (row0, row1) of 16-pixel tile rows this rank renders
+        # sync_group (ours only): process group over which backward sums the parameter gradients (overlapped exchange)
         rs = raster_settings
         args = (
             rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
@@ -93,6 +96,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         ctx.raster_settings = rs
         ctx.tile_band = tile_band
+        ctx.sync_group = sync_group
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, means3D, opacities, scales, rotations, cov3Ds_precomp, radii, sh, color,
                               geomBuffer, binningBuffer, imgBuffer)
@@ -112,13 +116,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:
-                grads8 = _C.rasterize_gaussians_backward(*args, tile_band=ctx.tile_band)
+                grads8 = _C.rasterize_gaussians_backward(*args, tile_band=ctx.tile_band, sync_group=ctx.sync_group)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise ex
         else:
-            grads8 = _C.rasterize_gaussians_backward(*args, tile_band=ctx.tile_band)
+            grads8 = _C.rasterize_gaussians_backward(*args, tile_band=ctx.tile_band, sync_group=ctx.sync_group)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
          grad_rotations) = grads8
         return (
@@ -130,6 +134,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_scales,
             grad_rotations,
             grad_cov3Ds_precomp,
+            None,
             None,
             None,
         )
@@ -259,12 +264,15 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings, tile_band=None):
+    def __init__(self, raster_settings, tile_band=None, sync_group=None):
         """tile_band (ours only): (row0, row1) band of 16-pixel tile rows rendered / differentiated by this rank when
-        one view is sharded across GPUs (stp_sharding.py); None = the whole image, as in the reference."""
+        one view is sharded across GPUs (stp_sharding.py); None = the whole image, as in the reference.
+        sync_group (ours only): torch.distributed process group; backward returns parameter gradients already summed
+        over the group, with the all-reduce overlapped with the preprocess-backward stage (_C.py)."""
         super().__init__()
         self.raster_settings = raster_settings
         self.tile_band = tile_band
+        self.sync_group = sync_group
 
     def markVisible(self, positions):
         # Mark visible points (based on frustum culling for camera) with a boolean
@@ -297,4 +305,4 @@ class GaussianRasterizer(nn.Module):
 
         # Invoke the CUDA rasterization routine
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                   raster_settings, self.tile_band)
+                                   raster_settings, self.tile_band, self.sync_group)

@@ -365,6 +365,44 @@ def test_long_tile_lists_sort_paths(P, order, min_len):
     assert (rr[1] - color).abs().max().item() <= TOL * rr[1].abs().max().item()
 
 
+def test_overlapped_gradient_exchange_matches_plain_backward(golden):
+    """sync_group: render backward + preprocess backward in Gaussian ranges with the all-reduce of each finished range
+    on a side stream (_C._backward_overlapped).  With a one-rank NCCL group the exchange is the identity, so the result
+    must equal the monolithic stp_backward (same kernels; tolerance = summation order of the atomics)."""
+    import torch.distributed as dist
+    from diff_gaussian_rasterization import _C
+    f = golden("global_default")
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
+                                device_id=_dev())
+        created = True
+    try:
+        dev = _dev()
+        s = f.scene
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        e = torch.empty(0, device=dev)
+        m3, sc, ro, op, sh = t(s["means3D"]), t(s["scales"]), t(s["rotations"]), t(s["opacities"]), t(f.shs())
+        vm, pm, iv, cp, bg = t(s["viewmatrix"]), t(s["projmatrix"]), t(s["inv_viewprojmatrix"]), t(s["campos"]), t(s["bg"])
+        tx, ty = float(s["tanfovx"]), float(s["tanfovy"])
+        out = _C.rasterize_gaussians(bg, m3, e, op, sc, ro, 1.0, e, vm, pm, iv, tx, ty, f.H, f.W, sh, f.deg, cp, False,
+                                     f.settings, False, False)
+        dL = t(s["dL_dout"])
+
+        def bwd(**kw):
+            return _C.rasterize_gaussians_backward(bg, m3, out[2], op, e, sc, ro, 1.0, e, vm, pm, iv, tx, ty, out[1], dL, sh,
+                                                   f.deg, cp, out[3], out[0], out[4], out[5], f.settings, False, **kw)
+        plain = bwd()
+        for chunks in (1, 3, 4):
+            over = bwd(sync_group=dist.group.WORLD, sync_chunks=chunks)
+            torch.cuda.synchronize()
+            for a, b in zip(plain, over):  # equal up to the summation order of the render-backward atomics
+                assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-30)
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
 def test_tile_band_sharding_reproduces_single_gpu_buffers(golden):
     """concatenating the per-band point lists / images of a tile-row sharding equals the
     single-GPU result bit for bit, and the summed band gradients equal the full gradients."""
