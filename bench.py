@@ -495,9 +495,11 @@ def main():
                      for k, v in stages.items() if k in ab}
         own = per_stage
         dom = max(own, key=lambda k: own[k]["ms"])
-        traffic = None
+        traffic = issue_pct = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(a.workload, {}).get(dom)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = prof.get(a.workload, {}).get(dom)
+            issue_pct = prof.get(a.workload + "_issue_active_pct", {}).get(dom)
         except Exception:
             pass
         line["roofline"] = {"bound": "hbm", "kernel": KERNEL_OF_STAGE[dom], "stage": dom,
@@ -505,6 +507,9 @@ def main():
                             "frac": per_stage[dom]["GBps"] / peak, "traffic": traffic,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                             "algorithmic_bytes": ab[dom], "kernel_ms": per_stage[dom]["ms"],
+                            # what actually bounds the dominant kernel (ncu smsp__issue_active of the committed capture,
+                            # profiles/*_ncu_full_summary_*.csv): the render kernels are instruction-issue bound, not HBM bound
+                            "issue_active_pct_ncu": issue_pct,
                             "stages": per_stage,
                             "whole_step": {"bytes": sum(ab.values()), "GBps": sum(ab.values()) / (ms_step * 1e-3) / 1e9,
                                            "frac": sum(ab.values()) / (ms_step * 1e-3) / 1e9 / peak}}

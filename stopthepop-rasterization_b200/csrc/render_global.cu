@@ -294,7 +294,8 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) v[k] = 0.f;
                 if (hit) {
-                    T = T / (1.f - alpha);
+                    const float inv_1ma = __frcp_rn(1.f - alpha);  // shared by the two divisions of backward.cu:541,571
+                    T = T * inv_1ma;
                     const float dchannel_dcolor = alpha * T;
                     const float c0 = s_rgb[0][j], c1 = s_rgb[1][j], c2 = s_rgb[2][j];
                     acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
@@ -309,7 +310,7 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
                     v[2] = dchannel_dcolor * g2;
                     dL_dalpha *= T;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    dL_dalpha += (-T_final * inv_1ma) * bg_dot;
                     const float dL_dG = co.w * dL_dalpha;
                     const float gdx = G * dx, gdy = G * dy;
                     const float dG_ddelx = -gdx * co.x - gdy * co.y;

@@ -30,7 +30,8 @@ if len(sys.argv) > 4:
                 "tile_sort": "Sort", "render_global_fwd": "Render", "render_global_bwd": "RenderBackward",
                 "render_hier_kernel": "Render", "render_hier_replay": "RenderBackward", "preprocess_bwd": "PreprocessBackward"}
     ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-    acc, cnt = {}, {}
+    ii, ti = hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active"), hdr.index("gpu__time_duration.sum")
+    acc, cnt, issue = {}, {}, {}
     for r in rows[2:]:
         for k, st in stage_of.items():
             if k in r[ki]:
@@ -39,11 +40,15 @@ if len(sys.argv) > 4:
                 a = acc[st].setdefault(kk, [0.0, 0])
                 a[0] += to_bytes(r[ri], units[ri]) + to_bytes(r[wi], units[wi])
                 a[1] += 1
+                dur = float(r[ti].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[ti], 1.0)
+                if dur >= issue.get(st, (0.0, 0.0))[0]:  # the longest kernel of the stage
+                    issue[st] = (dur, float(r[ii]))
                 break
     traffic = {st: sum(v[0] / v[1] for v in d.values()) for st, d in acc.items()}
     data = {}
     if os.path.exists(tj):
         data = json.load(open(tj))
     data[wl] = {k: round(v) for k, v in traffic.items()}
+    data[wl + "_issue_active_pct"] = {k: round(v[1], 1) for k, v in issue.items()}
     json.dump(data, open(tj, "w"), indent=1, sort_keys=True)
     print(json.dumps(data[wl]))
