@@ -226,7 +226,15 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     finally:
         gt, bt, it = geom.take(), binning.take(), img.take()
     if rc != 0:
-        raise RuntimeError(_err())
+        msg = _err()
+        if st.blend_record_cap > 0 and st.sort_mode != 1 and "image arena allocation failed" in msg:
+            # not enough memory for the blend log: it is an optimisation (except for PPX_FULL), render without it
+            torch.cuda.empty_cache()
+            return rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                                       cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy,
+                                       image_height, image_width, sh, degree, campos, prefiltered, settings_dict,
+                                       render_depth, debug, tile_band=tile_band, record_blends=False)
+        raise RuntimeError(msg)
     return n.value, out_color, radii, gt, bt, it
 
 

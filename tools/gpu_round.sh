@@ -9,8 +9,8 @@ python -c "import os; print('cpu cores', os.cpu_count())" >> $OUT/gpu.txt
 timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1
 tail -3 $OUT/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; tail -3 $OUT/smoke.log
-for w in C2 C3a C3b; do
-  S=100; [ $w != C2 ] && S=20
+for w in C2 C3a C3b C5 C4; do
+  S=100; [ $w != C2 ] && S=20; [ $w == C4 ] && S=3
   timeout 600 python bench.py --workload $w --impl reference --steps $S --warmup 5 > $OUT/bench_${w}_reference.json 2> $OUT/bench_${w}_reference.err
   NOCPU="--no-cpu-baseline"; [ $w == C2 ] && NOCPU=""
   timeout 600 python bench.py --workload $w --steps $S --warmup 5 $NOCPU > $OUT/bench_$w.json 2> $OUT/bench_$w.err
@@ -25,7 +25,7 @@ for arm in ("_reference", ""):
         print("$w", arm, "failed", e)
 PY
 done
-for w in C2 C3b; do
+for w in C2 C3b C4; do
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$w.csv \
       python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_$w.log 2>&1
 done
