@@ -534,14 +534,23 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
                 }
             }
         } else {
+            // my entries sit at list positions hl (< 16) and hl + 16: against the other half of the batch the
+            // position tie-break is decided, so half of the comparisons are a single '<' or '<='
 #pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float dj = nwd[j];
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    rk_new[s] += (dj < e_d[s]) || (dj == e_d[s] && j < cpos[s]);
-                    sh_res[s] += dj < r_d[s];
-                }
+                rk_new[0] += (dj < e_d[0]) || (dj == e_d[0] && j < hl);
+                rk_new[1] += dj <= e_d[1];
+                sh_res[0] += dj < r_d[0];
+                sh_res[1] += dj < r_d[1];
+            }
+#pragma unroll 8
+            for (int j = 16; j < 32; ++j) {
+                const float dj = nwd[j];
+                rk_new[0] += dj < e_d[0];
+                rk_new[1] += (dj < e_d[1]) || (dj == e_d[1] && (j - 16) < hl);
+                sh_res[0] += dj < r_d[0];
+                sh_res[1] += dj < r_d[1];
             }
         }
 #pragma unroll
