@@ -403,6 +403,80 @@ def test_overlapped_gradient_exchange_matches_plain_backward(golden):
             dist.destroy_process_group()
 
 
+OPTIONAL_INPUT_CASES = [
+    # (name, sort_mode, overrides)
+    ("sh_degree_0", 0, dict(degree=0)),
+    ("sh_degree_1", 3, dict(degree=1)),
+    ("sh_degree_2", 0, dict(degree=2)),
+    ("scale_modifier", 0, dict(scale_modifier=0.7)),
+    ("scale_modifier_hier", 3, dict(scale_modifier=1.3)),
+    ("colors_precomp", 0, dict(colors=True)),
+    ("colors_precomp_hier", 3, dict(colors=True)),
+    ("cov3D_precomp", 0, dict(cov=True)),
+]
+
+
+@pytest.mark.parametrize("name,mode,opt", OPTIONAL_INPUT_CASES, ids=[c[0] for c in OPTIONAL_INPUT_CASES])
+def test_optional_inputs_match_reference_build(name, mode, opt):
+    """The inputs a training loop varies besides the Gaussians themselves: active SH degree below the stored one (the
+    degree ramp of every 3DGS run, forward_common.h:20-70 / backward.cu:22-141), scale_modifier, colors_precomp instead
+    of SH (forward.cu:200, backward.cu:428-432) and cov3D_precomp instead of scales/rotations (forward.cu:126) --
+    forward and backward against the reference build on the same device (index buffers bit-exact, image / gradients
+    1e-5 or 10x the reference's own atomic noise)."""
+    from diff_gaussian_rasterization import _C
+    from oracle import ref_api as ref
+    import stp_scenes as S
+    if not ref.available():
+        pytest.skip("oracle/_ref not shipped")
+    dev = _dev()
+    W, H, P = 160, 96, 6000
+    sc, cam = S.make_scene(P, W, H, 501, sigma_scale=0.35)
+    sc, cam = S.to_device(sc, dev), S.to_device(cam, dev)
+    degree = opt.get("degree", 3)
+    sc = sc._replace(sh_degree=degree)
+    sm = opt.get("scale_modifier", 1.0)
+    e = torch.empty(0, device=dev)
+    g = torch.Generator().manual_seed(77)
+    colors = torch.rand(P, 3, generator=g).to(dev) if opt.get("colors") else None
+    cov = None
+    if opt.get("cov"):  # symmetric positive definite 3x3 from the scene's own scales / rotations, upper triangle
+        q = sc.rotations
+        r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                         2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                         2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).view(P, 3, 3)
+        M = R * sc.scales.view(P, 1, 3)
+        Sg = M @ M.transpose(1, 2)
+        cov = torch.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], 1).contiguous()
+    d = S.default_settings_dict(sort_mode=mode)
+    dL = S.make_upstream_grad(W, H, 4242).to(dev)
+    sh_in = e if colors is not None else sc.shs
+    col_in = colors if colors is not None else e
+    sc_in, ro_in, cov_in = (e, e, cov) if cov is not None else (sc.scales, sc.rotations, e)
+    out = _C.rasterize_gaussians(cam.bg, sc.means3D, col_in, sc.opacities, sc_in, ro_in, sm, cov_in, cam.viewmatrix,
+                                 cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx, cam.tanfovy, H, W, sh_in, degree,
+                                 cam.campos, False, d, False, False)
+    rr = ref.forward(sc, cam, d, colors_precomp=colors, cov3D_precomp=cov, scale_modifier=sm)
+    assert rr[0] == out[0]
+    assert torch.equal(rr[2], out[2])
+    assert torch.equal(ref.decode_binning(rr[4], rr[0])["point_list"], _C.view_binning(out[4], out[0])["point_list"])
+    assert (rr[1] - out[1]).abs().max().item() <= TOL * rr[1].abs().max().item()
+    mine = _C.rasterize_gaussians_backward(cam.bg, sc.means3D, out[2], sc.opacities, col_in, sc_in, ro_in, sm, cov_in,
+                                           cam.viewmatrix, cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx, cam.tanfovy,
+                                           out[1], dL, sh_in, degree, cam.campos, out[3], out[0], out[4], out[5], d, False)
+    rg = ref.backward(sc, cam, d, rr, dL, colors_precomp=colors, cov3D_precomp=cov, scale_modifier=sm)
+    rg2 = ref.backward(sc, cam, d, rr, dL, colors_precomp=colors, cov3D_precomp=cov, scale_modifier=sm)
+    for k, a, b, b2 in zip(GRAD_NAMES, mine, rg, rg2):
+        if b.numel() == 0:
+            continue
+        m = b.abs().max().item()
+        if m == 0.0:
+            assert a.abs().max().item() == 0.0, k
+            continue
+        noise = (b - b2).abs().max().item() / m
+        assert (a - b).abs().max().item() <= max(TOL, 10 * noise) * m, (k, (a - b).abs().max().item() / m, noise)
+
+
 def test_tile_band_sharding_reproduces_single_gpu_buffers(golden):
     """concatenating the per-band point lists / images of a tile-row sharding equals the
     single-GPU result bit for bit, and the summed band gradients equal the full gradients."""
