@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define STP_ABI_VERSION 3
+#define STP_ABI_VERSION 4
 
 /* replaces: enum SortMode / GlobalSortOrder, rasterizer.h:27-41 */
 enum { STP_SORT_GLOBAL = 0, STP_SORT_PPX_FULL = 1, STP_SORT_PPX_KBUFFER = 2, STP_SORT_HIER = 3 };
@@ -62,7 +62,12 @@ typedef struct StpSettings {
      * backward pass (8 B each, in the image arena; stp_image_bytes).  0 = none: backward repeats the re-sort.
      * Must have the same value in stp_forward and the matching stp_backward. */
     int32_t blend_record_cap;
+    /* replaces DebugVisualizationData::type (rasterizer_debug.h:11-20) as far as the Python API can reach it:
+     * 0 = disabled, STP_DEBUG_DEPTH = what render_depth=True selects (rasterize_points.cu:104-107): out_color becomes
+     * the Turbo-coloured, min/max-normalised accumulated depth.  Forward only; needs blend_record_cap > 0. */
+    int32_t debug_visualization;
 } StpSettings;
+#define STP_DEBUG_DEPTH 4 /* DebugVisualization::Depth */
 
 /* replaces: std::function<char*(size_t)> geometryBuffer/binningBuffer/imageBuffer,
  * rasterizer.h:195-198 (resizeFunctional, rasterize_points.cu:33-41).  Must return a device

@@ -39,7 +39,8 @@ def _e(device):
     return torch.empty(0, dtype=torch.float32, device=device)
 
 
-def forward(scene, cam, settings_dict, colors_precomp=None, cov3D_precomp=None, scale_modifier=1.0, debug=False):
+def forward(scene, cam, settings_dict, colors_precomp=None, cov3D_precomp=None, scale_modifier=1.0, debug=False,
+            render_depth=False):
     """scene/cam: stp_scenes.Scene/Camera already on the GPU.  Returns the reference's 6-tuple."""
     dev = scene.means3D.device
     C = module()
@@ -49,8 +50,8 @@ def forward(scene, cam, settings_dict, colors_precomp=None, cov3D_precomp=None, 
         _e(dev) if use_cov else scene.scales, _e(dev) if use_cov else scene.rotations, float(scale_modifier),
         cov3D_precomp if use_cov else _e(dev), cam.viewmatrix, cam.projmatrix, cam.inv_viewprojmatrix,
         cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width,
-        _e(dev) if colors_precomp is not None else scene.shs, scene.sh_degree, cam.campos, False, settings_dict, False,
-        debug)
+        _e(dev) if colors_precomp is not None else scene.shs, scene.sh_degree, cam.campos, False, settings_dict,
+        bool(render_depth), debug)
 
 
 def backward(scene, cam, settings_dict, fwd_out, dL_dout, colors_precomp=None, cov3D_precomp=None, scale_modifier=1.0,

@@ -62,8 +62,18 @@ bool convert_settings(const StpSettings* in, Settings& s, std::string& err, bool
     s.tile_based_culling = in->tile_based_culling != 0;
     s.hier_culling = in->hierarchical_4x4_culling != 0;
     s.proper_ewa_scaling = in->proper_ewa_scaling != 0;
-    s.rec_cap = (in->sort_mode != STP_SORT_PPX_KBUFFER && in->blend_record_cap > 0)
+    s.render_depth = !backward && in->debug_visualization == STP_DEBUG_DEPTH;
+    if (!backward && in->debug_visualization != 0 && in->debug_visualization != STP_DEBUG_DEPTH) {
+        err = "unsupported debug_visualization (only STP_DEBUG_DEPTH = render_depth is provided)";
+        return false;
+    }
+    // the k-buffer forward only writes a log for the depth visualisation (its backward re-sorts)
+    s.rec_cap = ((in->sort_mode != STP_SORT_PPX_KBUFFER || s.render_depth) && in->blend_record_cap > 0)
                     ? in->blend_record_cap : 0;
+    if (s.render_depth && s.rec_cap == 0) {
+        err = "render_depth needs the blend log (blend_record_cap > 0)";
+        return false;
+    }
     if (s.sort_mode == STP_SORT_HIER) {
         // instantiated queue sizes, forward.cu:445-480 / backward.cu:739-767
         if (s.q_mid != 8 && s.q_mid != 12 && s.q_mid != 20) {
@@ -364,6 +374,19 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     }
     g_launches += (s.sort_mode == STP_SORT_PPX_FULL) ? 2 : 1;
     timer.mark("Render");
+    if (s.render_depth) {  // rasterizer_impl.cu:402-413 (applyDebugVisualization) for DebugVisualization::Depth
+        STP_CUDA(launch_depth_visualisation(f, ra, s.sort_mode, means3D, g.counters, stream), "depth visualisation");
+        g_launches += 2;
+        uint32_t overflowed = 0;
+        cudaError_t e = cudaMemcpyAsync(&overflowed, g.counters + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return cuda_fail(e, "depth visualisation");
+        if (overflowed != 0)
+            return fail(STP_ERR_UNSUPPORTED, "render_depth: " + std::to_string(overflowed) +
+                                                 " pixels blended more than blend_record_cap entries; raise "
+                                                 "STP_BLEND_RECORD_CAP");
+        timer.mark("DepthVisualisation");
+    }
     timer.finish();
     return STP_OK;
 }

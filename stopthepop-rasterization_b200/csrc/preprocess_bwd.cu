@@ -102,11 +102,9 @@ preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
         a.dL_dopacity[idx] = 0.f;
 #pragma unroll
         for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * idx + k] = 0.f;
-        if (a.scales != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) a.dL_dscale[3 * idx + k] = 0.f;
-            reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int k = 0; k < 3; ++k) a.dL_dscale[3 * idx + k] = 0.f;
+        reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const bool rows_aligned = has_sh && ((reinterpret_cast<uintptr_t>(a.shs + (size_t)warp_base * n_sh) |
                                           reinterpret_cast<uintptr_t>(a.dL_dsh + (size_t)warp_base * n_sh)) & 15u) == 0;
@@ -406,6 +404,11 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
         dq.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) -
                4 * z * (dMt[1][1] + dMt[0][0]);
         reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
+    } else {  // cov3D_precomp: no scale / rotation gradient (the outputs are pure outputs, so they are still written)
+        a.dL_dscale[3 * idx] = 0.f;
+        a.dL_dscale[3 * idx + 1] = 0.f;
+        a.dL_dscale[3 * idx + 2] = 0.f;
+        reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 

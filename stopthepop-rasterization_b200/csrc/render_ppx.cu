@@ -66,6 +66,10 @@ render_kbuffer_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t contributor = 0;
+    // forward: blend log slot (only the depth visualisation asks the k-buffer forward for a log)
+    const uint32_t tile_lin_kb = (uint32_t)(tile_y * f.grid_x + tile_x);
+    const uint32_t rec_first = tile_lin_kb * (uint32_t)a.rec_cap * 256u + (uint32_t)tid;
+    uint32_t rec_idx = rec_first;
     float T_final = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f, bg_dot = 0.f;
     if constexpr (BWD) {
         if (inside) {
@@ -106,6 +110,11 @@ render_kbuffer_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             C1 = ffma(fmul(__ldg(colors + 3 * id + 1), alpha), T, C1);
             C2 = ffma(fmul(__ldg(colors + 3 * id + 2), alpha), T, C2);
             T = test_T;
+            if (a.blend_rec != nullptr) {
+                if (rec_idx < (tile_lin_kb + 1u) * (uint32_t)a.rec_cap * 256u)
+                    __stcs(a.blend_rec + rec_idx, make_uint2((uint32_t)id, __float_as_uint(alpha)));
+                rec_idx += 256u;
+            }
         } else {
             const float G = ws[0];
             const float4 co = __ldg(conic_opacity + id);
@@ -206,6 +215,7 @@ render_kbuffer_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             a.out_color[pix_id] = ffma(T, f.background[0], C0);
             a.out_color[plane + pix_id] = ffma(T, f.background[1], C1);
             a.out_color[2 * plane + pix_id] = ffma(T, f.background[2], C2);
+            if (a.blend_rec != nullptr) a.blend_count[pix_id] = (rec_idx - rec_first) >> 8;
         }
     }
 }

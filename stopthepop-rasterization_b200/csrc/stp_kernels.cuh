@@ -130,6 +130,10 @@ cudaError_t launch_render_kbuffer_bwd(const Frame& f, const Settings& s, const R
 cudaError_t launch_render_full_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream);
 cudaError_t launch_render_full_bwd(const Frame& f, const RenderBwdArgs& a, cudaStream_t stream);
 
+// depth_vis.cu: render_depth=True (DebugVisualization::Depth) from the blend log of the forward pass
+cudaError_t launch_depth_visualisation(const Frame& f, const RenderArgs& a, int sort_mode, const float* means3D,
+                                       uint32_t* counters, cudaStream_t stream);
+
 // preprocess_bwd.cu
 cudaError_t launch_preprocess_bwd(const PreprocessBwdArgs& a, const Frame& f, cudaStream_t stream);
 

@@ -35,7 +35,8 @@ struct GeometryState {
     float* rgb;
     uint32_t* tiles_touched;
     uint32_t* counters;  // [1] R (total instances), [2] error flags, [3] number of tiles on the large-tile sort list,
-                         // [4] pixels whose blend log overflowed in PPX_FULL mode
+                         // [4] pixels whose blend log overflowed in PPX_FULL mode, [5..7] depth visualisation: overflow
+                         // count, min and max of the accumulated depth (order-preserving integer images)
 
     static GeometryState from_chunk(char*& chunk, size_t P, bool inv) {
         GeometryState g;
@@ -132,7 +133,8 @@ struct Settings {
     int sort_mode, sort_order;
     int q_mid, q_head;
     bool rect_bounding, tight_opacity_bounding, tile_based_culling, hier_culling, proper_ewa_scaling;
-    int rec_cap;  // blend records per pixel (GLOBAL / HIER, 0 = none)
+    int rec_cap;  // blend records per pixel (0 = none)
+    bool render_depth;  // DebugVisualization::Depth instead of the colour image
     bool per_tile_depth() const { return sort_order == 2 || sort_order == 3; }
     bool requires_inv() const { return sort_mode != 0 || per_tile_depth(); }
 };

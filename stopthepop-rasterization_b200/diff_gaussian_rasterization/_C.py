@@ -34,7 +34,7 @@ class StpSettings(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "sort_mode", "sort_order", "queue_tile_4x4", "queue_tile_2x2", "queue_per_pixel", "rect_bounding",
         "tight_opacity_bounding", "tile_based_culling", "hierarchical_4x4_culling", "load_balancing",
-        "proper_ewa_scaling", "blend_record_cap")]
+        "proper_ewa_scaling", "blend_record_cap", "debug_visualization")]
 
 
 class StpTileBand(ctypes.Structure):
@@ -99,7 +99,7 @@ _lib.stp_backward_render.argtypes = list(_lib.stp_backward.argtypes)
 _lib.stp_backward_preprocess.restype = ctypes.c_int
 _lib.stp_backward_preprocess.argtypes = list(_lib.stp_backward.argtypes) + [ctypes.c_int, ctypes.c_int]
 
-if _lib.stp_abi_version() != 3:
+if _lib.stp_abi_version() != 4:
     raise ImportError("libstp_rasterizer.so ABI version mismatch")
 
 LIBRARY_PATH = _LIB_PATH
@@ -119,7 +119,10 @@ BLEND_RECORD_CAP = int(os.environ.get("STP_BLEND_RECORD_CAP", "256"))
 BLEND_RECORD_MODES = (0, 1, 3) if os.environ.get("STP_BLEND_RECORD_GLOBAL", "0") == "1" else (1, 3)
 
 
-def settings_from_dict(d, blend_record_cap=0):
+STP_DEBUG_DEPTH = 4  # DebugVisualization::Depth, rasterizer_debug.h:11-20
+
+
+def settings_from_dict(d, blend_record_cap=0, render_depth=False):
     """dict produced by ExtendedSettings.to_dict() -> StpSettings; every key mandatory like the
     reference's from_json (rasterizer.h:160-182 uses .at())."""
     ss, cs = d["sort_settings"], d["culling_settings"]
@@ -128,7 +131,8 @@ def settings_from_dict(d, blend_record_cap=0):
                        int(q["per_pixel"]), int(bool(cs["rect_bounding"])), int(bool(cs["tight_opacity_bounding"])),
                        int(bool(cs["tile_based_culling"])), int(bool(cs["hierarchical_4x4_culling"])),
                        int(bool(d["load_balancing"])), int(bool(d["proper_ewa_scaling"])),
-                       int(blend_record_cap) if int(ss["sort_mode"]) in BLEND_RECORD_MODES else 0)
+                       int(blend_record_cap) if (int(ss["sort_mode"]) in BLEND_RECORD_MODES or render_depth) else 0,
+                       STP_DEBUG_DEPTH if render_depth else 0)
 
 
 def _ptr(t):
@@ -194,11 +198,12 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     instead of sweeping the tile lists again / repeating the hierarchical re-sort; pass False for inference-only calls (GaussianRasterizer does, when no input requires a gradient)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:68-71
-    if render_depth:
-        raise RuntimeError("render_depth (debug visualisation) is outside the B200 hot path; see DESIGN.md")
     device = means3D.device
     P, H, W = means3D.size(0), int(image_height), int(image_width)
-    st = settings_from_dict(settings_dict, BLEND_RECORD_CAP if record_blends else 0)
+    cap = BLEND_RECORD_CAP if record_blends else 0
+    if render_depth and cap <= 0:  # the depth visualisation is computed from the blend log
+        cap = 256
+    st = settings_from_dict(settings_dict, cap, bool(render_depth))
     if P == 0:  # rasterize_points.cu:93
         e8 = torch.empty(0, dtype=torch.uint8, device=device)
         return (0, torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device),
@@ -227,7 +232,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         gt, bt, it = geom.take(), binning.take(), img.take()
     if rc != 0:
         msg = _err()
-        if st.blend_record_cap > 0 and st.sort_mode != 1 and "image arena allocation failed" in msg:
+        if (st.blend_record_cap > 0 and st.sort_mode != 1 and not render_depth and
+                "image arena allocation failed" in msg):
             # not enough memory for the blend log: it is an optimisation (except for PPX_FULL), render without it
             torch.cuda.empty_cache()
             return rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,

@@ -477,6 +477,33 @@ def test_optional_inputs_match_reference_build(name, mode, opt):
         assert (a - b).abs().max().item() <= max(TOL, 10 * noise) * m, (k, (a - b).abs().max().item() / m, noise)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_render_depth_matches_reference_build(mode):
+    """render_depth=True (DebugVisualization::Depth, rasterize_points.cu:104-107): Turbo-coloured, min/max-normalised
+    accumulated depth.  Here it is replayed from the blend log (depth_vis.cu); the reference compiles a second variant
+    of every render kernel.  Compared on the same device; the colormap's slope amplifies differences of the
+    normalised depth by up to ~8, hence 1e-4 absolute on colours in [0,1]."""
+    from diff_gaussian_rasterization import _C
+    from oracle import ref_api as ref
+    import stp_scenes as S
+    if not ref.available():
+        pytest.skip("oracle/_ref not shipped")
+    dev = _dev()
+    W, H, P = 200, 120, 5000
+    sc, cam = S.make_scene(P, W, H, 611, sigma_scale=0.4)
+    sc, cam = S.to_device(sc, dev), S.to_device(cam, dev)
+    d = S.default_settings_dict(sort_mode=mode, per_pixel=16 if mode == 2 else 4)
+    e = torch.empty(0, device=dev)
+    out = _C.rasterize_gaussians(cam.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e, cam.viewmatrix,
+                                 cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx, cam.tanfovy, H, W, sc.shs, 3,
+                                 cam.campos, False, d, True, False)
+    rr = ref.forward(sc, cam, d, render_depth=True)
+    assert rr[0] == out[0]
+    diff = (rr[1] - out[1]).abs()
+    assert diff.max().item() <= 1e-4, (diff.max().item(), int((diff > 1e-4).sum()))
+    assert out[1].min().item() >= 0.0 and out[1].max().item() <= 1.0 and out[1].std().item() > 0.01
+
+
 def test_tile_band_sharding_reproduces_single_gpu_buffers(golden):
     """concatenating the per-band point lists / images of a tile-row sharding equals the
     single-GPU result bit for bit, and the summed band gradients equal the full gradients."""
