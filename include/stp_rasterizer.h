@@ -87,7 +87,8 @@ typedef struct StpTileBand {
 /* replaces: CudaRasterizer::Rasterizer::forward, rasterizer.h:195-220 (impl rasterizer_impl.cu:221-413)
  * as called by RasterizeGaussiansCUDA, rasterize_points.cu:43-139.
  *   P Gaussians, D active SH degree, M SH coefficients per Gaussian (0 if shs==NULL).
- *   out_color  [3,H,W] f32 (must be zero-filled by the caller like torch::full, rasterize_points.cu:80)
+ *   out_color  [3,H,W] f32 (every pixel of the image -- of the band, with a tile band -- is written; with a band the
+ *              caller zero-fills the rest, like torch::full at rasterize_points.cu:80)
  *   radii      [P] i32     (written for every Gaussian; 0 = culled)
  *   num_rendered_out  HOST int: number of (tile,Gaussian) instances R (one stream sync, like
  *                     the reference's cudaMemcpy at rasterizer_impl.cu:317)
