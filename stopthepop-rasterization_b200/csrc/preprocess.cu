@@ -117,7 +117,10 @@ __device__ __forceinline__ void stage_sh_rows(const float* __restrict__ wsrc, in
 }  // namespace
 
 template <bool TBC>
-__global__ void __launch_bounds__(kPreprocessThreads)
+#ifndef STP_PRE_MINB
+#define STP_PRE_MINB 4  // 64 registers, 4 CTAs/SM: A/B on B200 (C5: 1.83 -> 1.47 ms)
+#endif
+__global__ void __launch_bounds__(kPreprocessThreads, STP_PRE_MINB)
 preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restrict__ tile_count) {
     extern __shared__ float s_sh[];  // [8 warps][32 rows][sh_stride]
 

@@ -75,7 +75,10 @@ __device__ __forceinline__ void move_sh_rows(float* __restrict__ gptr, int rows,
     }
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef STP_PREBWD_MINB
+#define STP_PREBWD_MINB 4  // 64 registers, 4 CTAs/SM: A/B on B200 (C2: 0.23 -> 0.16 ms, C5: 2.14 -> 1.48 ms)
+#endif
+__global__ void __launch_bounds__(256, STP_PREBWD_MINB)
 preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
     extern __shared__ float s_rows[];  // [8 warps][32 rows][3M+1]
     // Gaussians [a.first, a.P_end): the launch can cover a sub-range so that a data-parallel caller can start the
