@@ -55,8 +55,12 @@ __device__ __forceinline__ uint32_t strip_mask(float2 xy, float4 co, float tile_
     return mask;
 }
 
+// minBlocks = 1 lets ptxas keep the slab loop's addresses in registers: 0.35 -> 0.32 ms at C2 (A/B on B200; 6 and 8: 0.35)
+#ifndef STP_GLOBAL_FWD_MINB
+#define STP_GLOBAL_FWD_MINB 1
+#endif
 template <bool LOG>  // LOG: write the blend log (off by default for GLOBAL; the plain instantiation carries none of its code)
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, STP_GLOBAL_FWD_MINB)
 render_global_fwd_kernel(Frame f, RenderArgs a) {
     __shared__ float2 s_xy[kBlock];
     __shared__ float4 s_co[kBlock];
@@ -196,7 +200,7 @@ __device__ __forceinline__ int term_of_lane(int lane) {
     return ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock)  // A/B on B200: explicit minBlocks 1 / 5 / 6 are all slower (0.94 / 0.91 / 0.99 vs 0.89 ms)
 render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
     __shared__ uint32_t s_id[kBlock];
     __shared__ float2 s_xy[kBlock];
