@@ -276,7 +276,7 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
         const int rows = min(32, a.P - warp_base);
         if (rows > 0 && (reinterpret_cast<uintptr_t>(wsrc) & 15u) == 0 && surv != 0) {
             if (n_sh == 48)
-                stage_sh_rows<48>(wsrc, rows, 48, surv, lane, my_rows, stride);
+                move_sh_rows_48<false>(const_cast<float*>(wsrc), rows, surv, lane, my_rows);
             else
                 stage_sh_rows<0>(wsrc, rows, n_sh, surv, lane, my_rows, stride);
         } else {

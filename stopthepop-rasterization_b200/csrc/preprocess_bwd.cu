@@ -126,7 +126,10 @@ preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
     float* const my_rows = s_rows + (size_t)warp * 32 * sh_stride;
     const bool sh_staged = rows_aligned;
     if (sh_staged) {
-        move_sh_rows<false>(const_cast<float*>(a.shs) + (size_t)warp_base * n_sh, rows, n_sh, live, lane, my_rows, sh_stride);
+        if (n_sh == 48)
+            move_sh_rows_48<false>(const_cast<float*>(a.shs) + (size_t)warp_base * n_sh, rows, live, lane, my_rows);
+        else
+            move_sh_rows<false>(const_cast<float*>(a.shs) + (size_t)warp_base * n_sh, rows, n_sh, live, lane, my_rows, sh_stride);
         __syncwarp();
     }
     if (alive) {
@@ -141,7 +144,10 @@ preprocess_bwd_kernel(PreprocessBwdArgs a, Frame f) {
     if (sh_staged) {
         __syncwarp();
         const uint32_t all_rows = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
-        move_sh_rows<true>(a.dL_dsh + (size_t)warp_base * n_sh, rows, n_sh, all_rows, lane, my_rows, sh_stride);
+        if (n_sh == 48)
+            move_sh_rows_48<true>(a.dL_dsh + (size_t)warp_base * n_sh, rows, all_rows, lane, my_rows);
+        else
+            move_sh_rows<true>(a.dL_dsh + (size_t)warp_base * n_sh, rows, n_sh, all_rows, lane, my_rows, sh_stride);
     }
 }
 

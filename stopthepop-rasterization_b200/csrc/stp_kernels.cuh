@@ -99,6 +99,33 @@ __device__ __forceinline__ void accumulate_grads(float* __restrict__ acc, int id
 }
 #endif
 
+#ifdef __CUDACC__
+// SH degree 3 (48 floats per Gaussian): the 32 coefficient rows of a warp are one contiguous span of rows*12 float4.
+// Twelve fully unrolled steps, lane L moving float4 number L + 32 t: every float4 lies inside one row (48 % 4 == 0),
+// so there is no per-element bookkeeping, and the independent 128-bit loads of several steps are in flight together.
+// Shared-memory rows have an odd stride (49 floats) so that "lane r reads coefficient k of row r" is conflict-free.
+template <bool STORE>
+__device__ __forceinline__ void move_sh_rows_48(float* __restrict__ gptr, int rows, uint32_t live, int lane,
+                                                float* __restrict__ my_rows) {
+    float4* __restrict__ g4 = reinterpret_cast<float4*>(gptr);
+    const int n4 = rows * 12;
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+        const int i = lane + 32 * t;
+        const int row = i / 12, col = (i - row * 12) * 4;
+        if (i < n4 && ((live >> row) & 1u)) {
+            float* const dst = my_rows + row * 49 + col;
+            if constexpr (STORE) {
+                g4[i] = make_float4(dst[0], dst[1], dst[2], dst[3]);
+            } else {
+                const float4 v = __ldg(g4 + i);
+                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+            }
+        }
+    }
+}
+#endif
+
 cudaError_t launch_preprocess(const PreprocessArgs& a, const Frame& f, const GeometryState& g, uint32_t* tile_count,
                               bool tbc, cudaStream_t stream);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t stream);
