@@ -39,9 +39,8 @@ struct DupGaussian {
 
 // evaluates one tile of one Gaussian: returns whether a key is emitted and its depth.
 template <bool TBC, int ORDER>
-__device__ __forceinline__ bool eval_tile(const DupGaussian& gs, const RayCam& cam, int t, uint32_t grid_x,
+__device__ __forceinline__ bool eval_tile(const DupGaussian& gs, const RayCam& cam, int tx, int ty, uint32_t grid_x,
                                           uint32_t& tile_id, float& depth) {
-    const int tx = gs.x0 + t % gs.w, ty = gs.y0 + t / gs.w;
     tile_id = (uint32_t)ty * grid_x + (uint32_t)tx;
     const float tmin_x = (float)(tx * 16), tmin_y = (float)(ty * 16);
     const float tmax_x = (float)(tx * 16 + 15), tmax_y = (float)(ty * 16 + 15);
@@ -114,12 +113,35 @@ duplicate_kernel(int P, Frame f, GeometryState g, const int* __restrict__ radii,
         }
     }
 
-    // sequential head of the rectangle
-    for (int t = 0; t < min(gs.n, kSeqTiles); ++t) {
-        uint32_t tile_id;
-        float depth;
-        if (eval_tile<TBC, ORDER>(gs, cam, t, (uint32_t)f.grid_x, tile_id, depth))
-            emit_instance(cursor, bucket, cap, tile_id, depth, gs.idx);
+    // sequential head of the rectangle, four tiles at a time: the four slot claims (atomics with a return value, one
+    // L2 round trip each) are issued back to back before the first dependent store, and the tile walk is incremental
+    // (no integer division)
+    {
+        int tx = gs.x0, ty = gs.y0;
+        const int n_seq = min(gs.n, kSeqTiles);
+        for (int t0 = 0; t0 < n_seq; t0 += 4) {
+            uint32_t tile_id[4], slot[4];
+            float depth[4];
+            bool emit[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                emit[k] = false;
+                tile_id[k] = 0;
+                depth[k] = 0.f;
+                if (t0 + k < n_seq) {
+                    emit[k] = eval_tile<TBC, ORDER>(gs, cam, tx, ty, (uint32_t)f.grid_x, tile_id[k], depth[k]);
+                    if (++tx == gs.x0 + gs.w) {
+                        tx = gs.x0;
+                        ++ty;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) slot[k] = emit[k] ? atomicAdd(cursor + tile_id[k], 1u) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (emit[k] && slot[k] < cap) bucket[slot[k]] = ((uint64_t)__float_as_uint(depth[k]) << 32) | (uint64_t)gs.idx;
+        }
     }
 
     // warp-cooperative remainder
@@ -152,7 +174,7 @@ duplicate_kernel(int P, Frame f, GeometryState g, const int* __restrict__ radii,
         for (int t = kSeqTiles + lane; t < o.n; t += 32) {
             uint32_t tile_id = 0;
             float depth = 0.f;
-            if (eval_tile<TBC, ORDER>(o, cam, t, (uint32_t)f.grid_x, tile_id, depth))
+            if (eval_tile<TBC, ORDER>(o, cam, o.x0 + t % o.w, o.y0 + t / o.w, (uint32_t)f.grid_x, tile_id, depth))
                 emit_instance(cursor, bucket, cap, tile_id, depth, o.idx);
         }
     }
