@@ -324,6 +324,14 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     g_launches += 2;
     timer.mark("Preprocess");
 
+    // The binning arena is sized by R, which is only known after the preprocess kernel.  While that kernel runs, the
+    // arena is requested speculatively for 1.25x the previous call's R (the allocation callback goes through the
+    // caller's allocator, tens of microseconds); the carve-up below uses the exact R, so a generous buffer changes
+    // nothing, and a too small one is simply requested again.
+    static thread_local uint32_t last_R = 0;
+    const size_t guess = last_R ? (size_t)last_R + last_R / 4 + 4096 : 0;
+    char* bp = guess ? binning_alloc(binning_user, required<BinningState>(guess)) : nullptr;
+
     uint32_t R = 0;
     {
         cudaError_t e = cudaMemcpyAsync(&R, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
@@ -332,8 +340,9 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
         if (e != cudaSuccess) return cuda_fail(e, "num_rendered read-back");
     }
     if (num_rendered_out) *num_rendered_out = (int)R;
+    last_R = R;
 
-    char* bp = binning_alloc(binning_user, required<BinningState>((size_t)R));
+    if (bp == nullptr || (size_t)R > guess) bp = binning_alloc(binning_user, required<BinningState>((size_t)R));
     if (!bp) return fail(STP_ERR_ALLOC, "binning arena allocation failed");
     BinningState b = BinningState::from_chunk(bp, (size_t)R);
 
