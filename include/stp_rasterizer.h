@@ -112,7 +112,9 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user,
  * grad_accum [P,12] f32 is the only buffer the caller must zero-fill: the render-backward kernels accumulate the
  * screen-space gradients there, packed for 128-bit vector reductions ({conic.x, conic.y, conic.w, opacity | mean2D.x,
  * mean2D.y, color.r, color.g | color.b}; the reference zero-fills nine separate tensors, rasterize_points.cu:178-186).
- * All dL_* arrays are pure outputs and may be uninitialised -- every row is written, zeros for culled Gaussians:
+ * grad_accum and dL_drot must be 16-byte aligned (128-bit reductions / stores); shs and dL_dsh take a faster path
+ * when they are.  All dL_* arrays are pure outputs and may be uninitialised -- every row is written, zeros for culled
+ * Gaussians:
  * dL_dmean2D [P,3], dL_dopacity [P,1], dL_dcolor [P,3], dL_dmean3D [P,3], dL_dcov3D [P,6], dL_dsh [P,M,3],
  * dL_dscale [P,3], dL_drot [P,4].
  */

@@ -265,14 +265,12 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
     # contiguous, so a data-parallel caller can all-reduce them as one buffer (stp_sharding.py); the per-view
     # intermediates follow.
     widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 12]  # sh means3D scales rot opacity | means2D colors cov3D | accumulator
-    flat = torch.empty((sum(widths) * P,), dtype=torch.float32, device=device)
-    flat[sum(widths[:8]) * P:].zero_()
-    views, off = [], 0
-    for w in widths:
-        views.append(flat[off:off + w * P])
-        off += w * P
+    offs = slab_offsets(P, M)  # every sub-array starts on a 16-byte boundary (128-bit stores / vector reductions)
+    flat = torch.empty((offs[-1],), dtype=torch.float32, device=device)
+    flat[offs[8]:offs[8] + 12 * P].zero_()
+    views = [flat[offs[i]:offs[i] + widths[i] * P] for i in range(9)]
     dL_dsh, dL_dmeans3D, dL_dscales, dL_drot, dL_dopacity, dL_dmeans2D, dL_dcolors, dL_dcov3D, grad_accum = views
-    param_slab = flat[:sum(widths[:5]) * P]
+    param_slab = flat[:offs[5]]
     if P != 0:
         means3D = _f32(means3D, device)
         keep = [_f32(t, device) for t in (background, opacities, colors, scales, rotations, cov3D_precomp, viewmatrix,
@@ -292,13 +290,26 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
             if sync_group is None:
                 rc = _lib.stp_backward(*args)
             else:
-                rc = _backward_overlapped(args, P, M, dL_dsh, flat[3 * M * P:sum(widths[:5]) * P], sync_group,
+                rc = _backward_overlapped(args, P, M, dL_dsh, flat[offs[1]:offs[5]], sync_group,
                                           int(sync_chunks), device)
         if rc != 0:
             raise RuntimeError(_err())
     grads8 = (dL_dmeans2D.view(P, 3), dL_dcolors.view(P, NUM_CHANNELS), dL_dopacity.view(P, 1), dL_dmeans3D.view(P, 3),
               dL_dcov3D.view(P, 6), dL_dsh.view(P, M, 3), dL_dscales.view(P, 3), dL_drot.view(P, 4))
     return (grads8, param_slab) if want_param_slab else grads8
+
+
+def slab_offsets(P, M):
+    """float offsets of the nine sub-arrays of the backward slab (sh, means3D, scales, rot, opacity | means2D, colors,
+    cov3D | accumulator) and its total length; each start is rounded up to a multiple of 4 floats."""
+    widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 12]
+    offs, off = [], 0
+    for w in widths:
+        off = (off + 3) // 4 * 4
+        offs.append(off)
+        off += w * P
+    offs.append((off + 3) // 4 * 4)
+    return offs
 
 
 _comm_streams = {}

@@ -59,12 +59,21 @@ def all_reduce_param_grads(slab: torch.Tensor, group=None) -> torch.Tensor:
 
 def split_param_slab(slab: torch.Tensor, P: int, M: int):
     """views into the slab: (dL_dmeans3D[P,3], dL_dsh[P,M,3], dL_dopacity[P,1], dL_dscales[P,3], dL_drot[P,4])."""
-    widths = [3 * M, 3, 3, 4, 1]  # slab order of _C.rasterize_gaussians_backward: sh means3D scales rot opacity
-    out, off = [], 0
+    widths = [3 * M, 3, 3, 4, 1]  # slab order of _C.rasterize_gaussians_backward: sh means3D scales rot opacity,
+    out, off = [], 0              # every sub-array starting on a multiple of 4 floats (_C.slab_offsets)
     for w in widths:
+        off = (off + 3) // 4 * 4
         out.append(slab[off:off + w * P])
         off += w * P
     return out[1].view(P, 3), out[0].view(P, M, 3), out[4].view(P, 1), out[2].view(P, 3), out[3].view(P, 4)
+
+
+def param_slab_numel(P: int, M: int) -> int:
+    """length (floats) of the parameter-gradient slab for P Gaussians with M SH coefficients"""
+    off = 0
+    for w in (3 * M, 3, 3, 4, 1):
+        off = (off + 3) // 4 * 4 + w * P
+    return (off + 3) // 4 * 4
 
 
 def gather_image_bands(local_img: torch.Tensor, bands: Sequence[Tuple[int, int]], group=None) -> torch.Tensor:

@@ -51,7 +51,7 @@ def _worker(rank, world, port, q):
         full = sh.gather_image_bands(local, bands)
         ok_img = bool(torch.equal(full, truth))
         # parameter-gradient slab: sum over ranks, views alias the slab
-        n = (3 + 3 * M + 1 + 3 + 4) * P
+        n = sh.param_slab_numel(P, M)
         slab = torch.full((n,), float(rank + 1))
         sh.all_reduce_param_grads(slab)
         m3, shg, op, sc, ro = sh.split_param_slab(slab, P, M)
