@@ -413,6 +413,11 @@ OPTIONAL_INPUT_CASES = [
     ("colors_precomp", 0, dict(colors=True)),
     ("colors_precomp_hier", 3, dict(colors=True)),
     ("cov3D_precomp", 0, dict(cov=True)),
+    # fewer stored SH coefficients than 16 (generic staging path), odd P (rows not 16-byte aligned)
+    ("sh_M1_deg0", 3, dict(degree=0, M=1, P=6001)),
+    ("sh_M4_deg1", 0, dict(degree=1, M=4, P=6001)),
+    ("sh_M9_deg2", 0, dict(degree=2, M=9, P=5999)),
+    ("sh_M16_oddP", 3, dict(P=6001)),
 ]
 
 
@@ -429,8 +434,10 @@ def test_optional_inputs_match_reference_build(name, mode, opt):
     if not ref.available():
         pytest.skip("oracle/_ref not shipped")
     dev = _dev()
-    W, H, P = 160, 96, 6000
+    W, H, P = 160, 96, opt.get("P", 6000)
     sc, cam = S.make_scene(P, W, H, 501, sigma_scale=0.35)
+    if "M" in opt:
+        sc = sc._replace(shs=sc.shs[:, :opt["M"]].contiguous())
     sc, cam = S.to_device(sc, dev), S.to_device(cam, dev)
     degree = opt.get("degree", 3)
     sc = sc._replace(sh_degree=degree)
