@@ -264,8 +264,10 @@ def main():
     pixels = W * H
     bands_mode = a.workload in BAND_SHARDED
 
-    from oracle import ref_api as ref
-    use_ref_gpu = a.impl == "reference" and ref.available() and torch.cuda.is_available()
+    ref, use_ref_gpu = None, False
+    if a.impl == "reference":  # the only arm that touches oracle/ (besides the cpu_baseline leg below)
+        from oracle import ref_api as ref
+        use_ref_gpu = ref.available() and torch.cuda.is_available()
 
     if a.impl == "reference" and not use_ref_gpu:
         # no reference CUDA build travelled with the repo: the C oracle port on the host cores

@@ -576,8 +576,10 @@ def test_tile_band_sharding_reproduces_single_gpu_buffers(golden):
         assert (s - full["grads"][k]).abs().max().item() <= 1e-5 * m
 
 
-def test_autograd_api_end_to_end(golden):
-    """GaussianRasterizer through torch.autograd returns gradients in input order (__init__.py:160-172)."""
+@pytest.mark.parametrize("debug", [False, True])
+def test_autograd_api_end_to_end(golden, debug):
+    """GaussianRasterizer through torch.autograd returns gradients in input order (__init__.py:160-172); debug=True is the
+    reference's per-stage synchronise-and-check mode (auxiliary.h:246-253)."""
     from diff_gaussian_rasterization import ExtendedSettings, GaussianRasterizationSettings, GaussianRasterizer
     f = golden("global_default")
     dev = _dev()
@@ -585,7 +587,7 @@ def test_autograd_api_end_to_end(golden):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     rs = GaussianRasterizationSettings(f.H, f.W, float(s["tanfovx"]), float(s["tanfovy"]), t(s["bg"]), 1.0,
                                        t(s["viewmatrix"]), t(s["projmatrix"]), t(s["inv_viewprojmatrix"]), f.deg,
-                                       t(s["campos"]), False, ExtendedSettings.from_dict(f.settings), False, False)
+                                       t(s["campos"]), False, ExtendedSettings.from_dict(f.settings), False, debug)
     leaves = [t(a).requires_grad_(True) for a in (s["means3D"], s["opacities"], f.shs(), s["scales"], s["rotations"])]
     m3, op, sh, sc, ro = leaves
     m2 = torch.zeros_like(m3, requires_grad=True)
