@@ -157,47 +157,68 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
     }
 }
 
-// Sum v[0..8] over the 32 lanes with a recursive-halving exchange: after the five steps the total of
-// term k sits in lane kTermLane(k).  16 shuffles instead of 9 x 5.
-__device__ __forceinline__ float reduce9(float (&v)[9], int lane) {
-    // step 1 (xor 16): lower half keeps terms 0..7, upper half keeps term 8
-    const bool up16 = lane & 16;
-    float w[8];
+// Sum v[0..8] over the 32 lanes with a BALANCED recursive-halving exchange: every step splits the terms a lane is still
+// responsible for as evenly as possible between the two halves of its group (9 -> 5|4 -> 3|2, 2|2 -> ...), so the five
+// steps cost 5 + 3 + 2 + 1 + 1 = 12 shuffles (a plain butterfly: 45; halving that parks term 8 in the upper half: 16).
+// Afterwards the total of term t sits in every lane of its owner group:
+//   t = 0: lanes 0-1, t = 1: lanes 2-3, t = 2: lanes 4-7, t = 3: 8-11, t = 4: 12-15, t = 5: 16-19, ..., t = 8: 28-31.
+__device__ __forceinline__ float reduce9(const float (&v)[9], int lane) {
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+    // step A (xor 16): lower half keeps terms 0..4, upper half terms 5..8
+    float a[5];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float send = up16 ? v[i] : ((i == 0) ? v[8] : 0.0f);
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-        w[i] = (up16 ? ((i == 0) ? v[8] : 0.0f) : v[i]) + recv;
+    for (int i = 0; i < 5; ++i) {
+        const float mine = b16 ? (i < 4 ? v[5 + i] : 0.0f) : v[i];
+        const float send = b16 ? v[i] : (i < 4 ? v[5 + i] : 0.0f);
+        a[i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
     }
-    // lower half: w[0..7] = terms 0..7 ; upper half: w[0] = term 8, w[1..7] = 0
-    // step 2 (xor 8): keep 4 of 8
-    const bool up8 = lane & 8;
-    float x[4];
+    // step B (xor 8): lower half: bit3 clear keeps a0..a2, set keeps a3,a4; upper half: a0,a1 | a2,a3
+    float c[3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float recv = __shfl_xor_sync(0xffffffffu, up8 ? w[i] : w[4 + i], 8);
-        x[i] = (up8 ? w[4 + i] : w[i]) + recv;
+    for (int i = 0; i < 3; ++i) {
+        // value kept at position i and value sent at position i (what the partner keeps at its position i)
+        const float keep_lo = a[i];                                    // bit3 clear: lower keeps a0..a2, upper a0,a1(,0)
+        const float keep_hi = b16 ? (i < 2 ? a[2 + i] : 0.0f) : (i < 2 ? a[3 + i] : 0.0f);  // bit3 set
+        const float mine = b8 ? keep_hi : ((b16 && i == 2) ? 0.0f : keep_lo);
+        const float send = b8 ? ((b16 && i == 2) ? 0.0f : keep_lo) : keep_hi;
+        c[i] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
     }
-    // step 3 (xor 4): keep 2 of 4
-    const bool up4 = lane & 4;
-    float y[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float recv = __shfl_xor_sync(0xffffffffu, up4 ? x[i] : x[2 + i], 4);
-        y[i] = (up4 ? x[2 + i] : x[i]) + recv;
+    // groups now: (b16,b8) = (0,0): c0..c2 = terms 0,1,2; (0,1): c0,c1 = terms 3,4; (1,0): terms 5,6; (1,1): terms 7,8
+    // step C (xor 4): group (0,0): bit2 clear keeps c0,c1, set keeps c2; the other groups: clear keeps c0, set keeps c1
+    const bool g00 = !b16 && !b8;
+    float d[2];
+    {
+        const float keep_lo0 = c[0], keep_lo1 = g00 ? c[1] : 0.0f;   // bit2 clear
+        const float keep_hi0 = g00 ? c[2] : c[1];                    // bit2 set (position 1 unused)
+        const float mine0 = b4 ? keep_hi0 : keep_lo0, send0 = b4 ? keep_lo0 : keep_hi0;
+        const float mine1 = b4 ? 0.0f : keep_lo1, send1 = b4 ? keep_lo1 : 0.0f;
+        d[0] = mine0 + __shfl_xor_sync(0xffffffffu, send0, 4);
+        d[1] = mine1 + __shfl_xor_sync(0xffffffffu, send1, 4);
     }
-    // step 4 (xor 2): keep 1 of 2
-    const bool up2 = lane & 2;
-    const float recv2 = __shfl_xor_sync(0xffffffffu, up2 ? y[0] : y[1], 2);
-    float z = (up2 ? y[1] : y[0]) + recv2;
-    // step 5 (xor 1): both lanes of a pair end with the total
+    // only group (b16,b8,b4) = (0,0,0) still holds two terms (0 and 1)
+    // step D (xor 2)
+    const bool g000 = g00 && !b4;
+    const float mineD = (g000 && b2) ? d[1] : d[0];
+    const float sendD = g000 ? (b2 ? d[0] : d[1]) : d[0];
+    float z = mineD + __shfl_xor_sync(0xffffffffu, sendD, 2);
+    // step E (xor 1)
     z += __shfl_xor_sync(0xffffffffu, z, 1);
     return z;
 }
-// term index whose total lane `lane` holds after reduce9 (lanes 16..31 hold term 8 in the lanes with bits 8,4,2 clear)
+// term whose total this lane adds to the accumulator after reduce9 (one lane per owner group), -1 for the others
 __device__ __forceinline__ int term_of_lane(int lane) {
-    if (lane & 16) return ((lane & 14) == 0) ? 8 : -1;
-    return ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    switch (lane) {
+        case 0: return 0;
+        case 2: return 1;
+        case 4: return 2;
+        case 8: return 3;
+        case 12: return 4;
+        case 16: return 5;
+        case 20: return 6;
+        case 24: return 7;
+        case 28: return 8;
+        default: return -1;
+    }
 }
 
 __global__ void __launch_bounds__(kBlock)  // A/B on B200: explicit minBlocks 1 / 5 / 6 are all slower (0.94 / 0.91 / 0.99 vs 0.89 ms)
@@ -298,7 +319,8 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) v[k] = 0.f;
                 if (hit) {
-                    const float inv_1ma = __frcp_rn(1.f - alpha);  // shared by the two divisions of backward.cu:541,571
+                    // one reciprocal (MUFU.RCP, 1 ulp) shared by the two divisions of backward.cu:541,571
+                    const float inv_1ma = __fdividef(1.f, 1.f - alpha);
                     T = T * inv_1ma;
                     const float dchannel_dcolor = alpha * T;
                     const float c0 = s_rgb[0][j], c1 = s_rgb[1][j], c2 = s_rgb[2][j];
@@ -327,7 +349,7 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
                     v[8] = G * dL_dalpha;
                 }
                 const float tot = reduce9(v, lane);
-                if (my_term >= 0 && !(lane & 1)) atomicAdd(&s_acc[j][my_term], tot);
+                if (my_term >= 0) atomicAdd(&s_acc[j][my_term], tot);
             }
         }
         __syncthreads();
