@@ -92,3 +92,36 @@ def test_settings_dict_keys_are_mandatory():  # rasterizer.h:160-182 uses .at()
     del d["load_balancing"]
     with pytest.raises(KeyError):
         dgr._C.settings_from_dict(d)
+
+
+def test_backward_slab_layout_is_aligned_and_matches_sharding_helper():
+    """every sub-array of the backward slab starts on a 16-byte boundary for any P (vector reductions / float4 stores),
+    the five parameter gradients form one contiguous prefix, and stp_sharding.split_param_slab reads the same layout"""
+    import stp_sharding as sh
+    from diff_gaussian_rasterization import _C
+    for P, M in ((1, 16), (3, 16), (7, 4), (1025, 1), (6001, 9), (4096, 16), (5, 0)):
+        offs = _C.slab_offsets(P, M)
+        widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 12]
+        assert all(o % 4 == 0 for o in offs)
+        assert all(offs[i] + widths[i] * P <= offs[i + 1] for i in range(9))
+        assert offs[5] == sh.param_slab_numel(P, M)
+        slab = torch.arange(offs[5], dtype=torch.float32)
+        m3, shg, op, sc, ro = sh.split_param_slab(slab, P, M)
+        assert shg.shape == (P, M, 3) and m3.shape == (P, 3) and op.shape == (P, 1)
+        if M:
+            assert shg.reshape(-1)[0].item() == offs[0]
+        assert m3.reshape(-1)[0].item() == offs[1] and sc.reshape(-1)[0].item() == offs[2]
+        assert ro.reshape(-1)[0].item() == offs[3] and op.reshape(-1)[0].item() == offs[4]
+
+
+def test_blend_log_capacity_is_recovered_from_the_arena_size():
+    """backward learns the capacity of the forward pass's blend log from the size of the image arena alone"""
+    from diff_gaussian_rasterization import _C
+    for W, H in ((64, 48), (1920, 1080), (17, 5)):
+        for cap in (0, 1, 6, 256):
+            nbytes = _C._lib.stp_image_bytes(W, H, cap)
+
+            class _Buf:  # only numel() is consulted; no need to allocate gigabytes here
+                def numel(self):
+                    return nbytes
+            assert _C.blend_record_cap_of(_Buf(), W, H) == cap
