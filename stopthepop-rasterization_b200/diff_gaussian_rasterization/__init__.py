@@ -81,6 +81,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.settings.to_dict(), rs.render_depth,
             rs.debug,
         )
+        ctx.settings_dict = args[19]  # backward uses the settings the forward pass ran with
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
             try:
@@ -111,7 +112,7 @@ class _RasterizeGaussians(torch.autograd.Function):
          binningBuffer, imgBuffer) = ctx.saved_tensors
         args = (rs.bg, means3D, radii, opacities, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 rs.viewmatrix, rs.projmatrix, rs.inv_viewprojmatrix, rs.tanfovx, rs.tanfovy, color, grad_out_color, sh,
-                rs.sh_degree, rs.campos, geomBuffer, num_rendered, binningBuffer, imgBuffer, rs.settings.to_dict(),
+                rs.sh_degree, rs.campos, geomBuffer, num_rendered, binningBuffer, imgBuffer, ctx.settings_dict,
                 rs.debug)
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)
@@ -204,7 +205,21 @@ class ExtendedSettings:
     proper_ewa_scaling: bool = False
 
     def to_dict(self):
-        return asdict(self, dict_factory=enum_dict_factory)
+        # same result as asdict(self, dict_factory=enum_dict_factory) (the reference, __init__.py:231), written out:
+        # this runs twice per training step and the generic recursive asdict costs ~25 us
+        ss, cs, q = self.sort_settings, self.culling_settings, self.sort_settings.queue_sizes
+        val = lambda v: v.value if isinstance(v, IntEnum) else v  # noqa: E731
+        return {
+            "sort_settings": {
+                "queue_sizes": {"tile_4x4": val(q.tile_4x4), "tile_2x2": val(q.tile_2x2), "per_pixel": val(q.per_pixel)},
+                "sort_mode": val(ss.sort_mode), "sort_order": val(ss.sort_order)},
+            "culling_settings": {
+                "rect_bounding": val(cs.rect_bounding), "tight_opacity_bounding": val(cs.tight_opacity_bounding),
+                "tile_based_culling": val(cs.tile_based_culling),
+                "hierarchical_4x4_culling": val(cs.hierarchical_4x4_culling)},
+            "load_balancing": val(self.load_balancing),
+            "proper_ewa_scaling": val(self.proper_ewa_scaling),
+        }
 
     def to_json(self):
         return json.dumps(self.to_dict())
