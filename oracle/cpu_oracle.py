@@ -110,8 +110,12 @@ class Oracle:
         self.final_T = arr(s.final_T, N, np.float32).reshape(self.H, self.W)
         self.n_contrib = arr(s.n_contrib, N, np.int64).astype(np.int32).reshape(self.H, self.W)
 
-    def backward(self, dL_dout, pixel_colors=None):
+    def backward(self, dL_dout, pixel_colors=None, full_sort_ext=False):
+        """full_sort_ext=True: PPX_FULL backward, which the reference does NOT have (backward.cu:733-736) -- the derived
+        extension of stp_oracle.c:render_full (same per-pixel order as the forward pass, the reference's front-to-back
+        gradient terms), used to pin the CUDA path's replay backward."""
         P, M = self.P, self.M
+        lib().orc_allow_full_backward_ext(1 if full_sort_ext else 0)
         pc = _c(self.out_color if pixel_colors is None else pixel_colors)
         dl = _c(dL_dout)
         z = lambda *s: np.zeros(s, dtype=np.float32)  # noqa: E731

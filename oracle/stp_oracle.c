@@ -755,7 +755,10 @@ static int fs_cmp(const void* a, const void* b) {
     if (x->k > y->k) return 1;
     return x->ord - y->ord;
 }
-static void render_full(const OrcInputs* in, OrcState* st) {
+/* bwd != NULL: NOT in the reference (it has no PPX_FULL backward, backward.cu:733-736).  Derived extension used to pin
+ * the CUDA path's replay backward: the same per-pixel order as the forward pass, with the front-to-back gradient terms
+ * the reference uses for its k-buffer / hierarchical backward (blend_bwd_front_to_back). */
+static void render_full(const OrcInputs* in, OrcState* st, BwdCtx* bwd) {
     const int W = in->W, H = in->H, gx = (W + 15) / 16;
 #pragma omp parallel for schedule(dynamic, 16)
     for (int pid = 0; pid < W * H; ++pid) {
@@ -772,6 +775,8 @@ static void render_full(const OrcInputs* in, OrcState* st) {
                 else { e->k = FLT_MAX; e->v = -1; }
             }
         float T = 1.0f, C[3] = {0, 0, 0}; uint32_t contributor = 0, last = 0; int done = 0, todo = n;
+        Pix bp;
+        if (bwd) pix_init(in, st, bwd, &bp, px, py);
         for (int r = 0; r < rounds; ++r, todo -= 256) {
             for (int t = 0; t < 256; ++t) {
                 const int idx = (r + 3) * 256 + t;
@@ -794,8 +799,13 @@ static void render_full(const OrcInputs* in, OrcState* st) {
                 const float dx = st->means2D[2 * id] - (float)px, dy = st->means2D[2 * id + 1] - (float)py;
                 const float pw = opacity_factor(dx, dy, co[0], co[1], co[2]);
                 if (pw < 0.0f) continue;
-                const float alpha = fminf(0.99f, co[3] * expf(-pw));
+                const float G = expf(-pw);
+                const float alpha = fminf(0.99f, co[3] * G);
                 if (alpha < ALPHA_THRESHOLD) continue;
+                if (bwd) {
+                    if (!blend_bwd_front_to_back(in, st, bwd, &bp, px, py, id, G)) done = 1;
+                    continue;
+                }
                 const float test_T = T * (1.0f - alpha);
                 if (test_T < T_THRESHOLD) { done = 1; continue; }
                 for (int ch = 0; ch < 3; ++ch) C[ch] += st->rgb[3 * id + ch] * alpha * T;
@@ -804,6 +814,7 @@ static void render_full(const OrcInputs* in, OrcState* st) {
             }
             memcpy(win, keep, sizeof(keep));
         }
+        if (bwd) continue; /* the forward outputs stay as they are */
         st->final_T[pid] = T;
         st->n_contrib[pid] = last;
         for (int ch = 0; ch < 3; ++ch) st->out_color[(size_t)ch * W * H + pid] = C[ch] + T * in->bg[ch];
@@ -1013,19 +1024,26 @@ OrcState* orc_forward(const OrcInputs* in, const OrcSettings* s) { /* Rasterizer
     binning(in, s, st);
     switch (s->sort_mode) {
         case 0: render_global(in, st); break;
-        case 1: render_full(in, st); break;
+        case 1: render_full(in, st, NULL); break;
         case 2: render_kbuffer(in, s, st, NULL); break;
         default: render_hier(in, s, st, NULL); break;
     }
     return st;
 }
+/* off: mirror the reference (PPX_FULL backward is an error); on: the derived extension of render_full above */
+static int g_allow_full_backward_ext = 0;
+void orc_allow_full_backward_ext(int on) { g_allow_full_backward_ext = on; }
+
 /* Rasterizer::backward, rasterizer_impl.cu:417-526; all outputs zero-filled by the caller */
 int orc_backward(const OrcInputs* in, const OrcSettings* s, OrcState* st, const float* pixel_colors, const float* dL_dpix, float* dmean2D,
                  float* dconic, float* dopacity, float* dcolor, float* dmean3D, float* dcov3D, float* dsh, float* dscale, float* drot) {
     BwdCtx b = {dmean2D, dconic, dopacity, dcolor, dL_dpix, pixel_colors};
     switch (s->sort_mode) {
         case 0: render_global_bwd(in, st, &b); break;
-        case 1: return -2; /* "Backward not supported for full per-pixel sort", backward.cu:735 */
+        case 1:
+            if (!g_allow_full_backward_ext) return -2; /* "Backward not supported for full per-pixel sort", backward.cu:735 */
+            render_full(in, st, &b);
+            break;
         case 2: render_kbuffer(in, s, st, &b); break;
         default: render_hier(in, s, st, &b); break;
     }

@@ -602,3 +602,20 @@ def test_autograd_api_end_to_end(golden, debug):
         assert rel <= max(TOL, 10 * float(f.fx[name + "_noise"])), (name, rel)
     vis = rast.markVisible(m3.detach())
     assert vis.dtype == torch.bool and int(vis.sum()) >= int((radii > 0).sum())
+
+
+@pytest.mark.parametrize("name", ["full_sort", "full_sort_long"])
+def test_full_sort_backward_matches_oracle_extension(golden, name):
+    """PPX_FULL backward by replay against the CPU oracle's derived extension (oracle/stp_oracle.c:render_full with a
+    BwdCtx; pinned on the CPU by finite differences and by k-buffer equivalence, tests/test_oracle_golden.py).  Unlike
+    test_full_sort_backward_by_replay this also covers tile lists longer than 1024 entries, where the blending order is
+    the reference's sliding-window order rather than an exact sort.  There is no reference gradient for this mode; the
+    oracle evaluates exp() on the host, hence 5e-5 instead of 1e-5."""
+    f = golden(name)
+    r = run_ours(f, backward=True, record_cap=1024)
+    o = f.oracle()
+    ref = o.backward(f.scene["dL_dout"], f.fx["out_color"], full_sort_ext=True)
+    for k in GRAD_NAMES:
+        a, b = npy(r["grads"][k]).reshape(-1), ref[k].reshape(-1)
+        rel = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+        assert rel <= 5e-5, (k, rel)

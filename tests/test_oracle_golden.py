@@ -99,3 +99,47 @@ def test_oracle_hier_cull_fd(golden):
         assert abs(fd - an) <= 1e-2 * abs(an), (i, fd, an)
     # the documented reference defect: its stored gradient for Gaussian 668 is an order of magnitude off
     assert abs(float(f.fx["dL_dopacity"][668, 0]) - float(g["dL_dopacity"][668, 0])) > 1.0
+
+
+def _scene_oracle(P, W, H, seed, sigma, settings, opacities=None):
+    import stp_scenes as S
+    from oracle import cpu_oracle as co
+    sc, cam = S.make_scene(P, W, H, seed, sigma_scale=sigma)
+    op = sc.opacities.numpy() if opacities is None else opacities
+    o = co.Oracle(settings, sc.means3D.numpy(), sc.scales.numpy(), sc.rotations.numpy(), op, sc.shs.numpy(), 3,
+                  cam.viewmatrix.numpy(), cam.projmatrix.numpy(), cam.inv_viewprojmatrix.numpy(), cam.campos.numpy(),
+                  cam.bg.numpy(), cam.tanfovx, cam.tanfovy, W, H)
+    return o, sc, cam
+
+
+def test_oracle_full_sort_backward_extension():
+    """PPX_FULL backward is not in the reference (backward.cu:733-736); the oracle mirrors that (RuntimeError) unless the
+    derived extension is asked for.  The extension is pinned two ways: (1) where FULL and KBUFFER(24) forward images
+    coincide, it must equal the oracle's k-buffer backward (itself pinned against the reference's gradients by the
+    golden fixtures); (2) central finite differences of the oracle's own PPX_FULL forward."""
+    import stp_scenes as S
+    W, H, P, seed, sigma = 64, 48, 1500, 12, 0.5
+    d_full, d_kb = S.default_settings_dict(sort_mode=1), S.default_settings_dict(sort_mode=2, per_pixel=24)
+    dL = S.make_upstream_grad(W, H, 3000 + seed).numpy()
+    of, sc, cam = _scene_oracle(P, W, H, seed, sigma, d_full)
+    ok, _, _ = _scene_oracle(P, W, H, seed, sigma, d_kb)
+    with pytest.raises(RuntimeError, match="Backward not supported for full per-pixel sort"):
+        of.backward(dL)
+    assert np.abs(of.out_color - ok.out_color).max() <= 1e-6
+    gf, gk = of.backward(dL, full_sort_ext=True), ok.backward(dL)
+    for k in gk:
+        m = max(np.abs(gk[k]).max(), 1e-30)
+        assert np.abs(gf[k] - gk[k]).max() <= 1e-5 * m, k
+    # finite differences in opacity for the Gaussians with the largest gradients
+    g = gf["dL_dopacity"][:, 0]
+    eps = 1e-3
+    base_op = sc.opacities.numpy()
+    for i in np.argsort(-np.abs(g))[:4]:
+        lo_hi = []
+        for sgn in (+1, -1):
+            op = base_op.copy()
+            op[i, 0] += sgn * eps
+            oo, _, _ = _scene_oracle(P, W, H, seed, sigma, d_full, opacities=op)
+            lo_hi.append(float((oo.out_color.astype(np.float64) * dL).sum()))
+        fd = (lo_hi[0] - lo_hi[1]) / (2 * eps)
+        assert abs(fd - g[i]) <= 2e-2 * abs(g[i]), (i, fd, g[i])
