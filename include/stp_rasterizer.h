@@ -188,7 +188,7 @@ typedef struct StpGeometryView {
     uint32_t* tiles_touched; /* [P]   u32                                              */
 } StpGeometryView;
 typedef struct StpBinningView {
-    uint32_t* point_list;        /* [R] u32 sorted Gaussian ids (0xFFFFFFFF = padding)  */
+    uint32_t* point_list;        /* [R] u32 sorted Gaussian ids                         */
     uint64_t* point_list_keys;   /* [R] u64 sorted (tile<<32 | depth bits) keys          */
 } StpBinningView;
 typedef struct StpImageView {
@@ -215,7 +215,7 @@ int stp_last_timings(float* ms, const char** names, int max_n);
 int stp_timing_summary(float* mean_ms, const char** names, int* counts, int max_n);
 void stp_timing_reset(void);
 /* cumulative number of hand-written kernels this thread has launched through stp_forward/stp_backward
- * (library kernels such as a CUB sort are NOT counted) -- bench.py reports the per-step difference. */
+ * (there is no library kernel on the path; memsets are not counted) -- bench.py reports the per-step difference. */
 long long stp_kernel_launches(void);
 
 const char* stp_last_error(void);
