@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define STP_ABI_VERSION 4
+#define STP_ABI_VERSION 5
 
 /* replaces: enum SortMode / GlobalSortOrder, rasterizer.h:27-41 */
 enum { STP_SORT_GLOBAL = 0, STP_SORT_PPX_FULL = 1, STP_SORT_PPX_KBUFFER = 2, STP_SORT_HIER = 3 };
@@ -117,8 +117,12 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user,
  * Gaussians:
  * dL_dmean2D [P,3], dL_dopacity [P,1], dL_dcolor [P,3], dL_dmean3D [P,3], dL_dcov3D [P,6], dL_dsh [P,M,3],
  * dL_dscale [P,3], dL_drot [P,4].
+ * binning_bytes: size of the binning arena as the allocation callback of stp_forward was (last) asked for it.  The
+ * reference passes num_rendered (R) here to re-derive the carve-up (rasterizer_impl.cu:449); this library carves the
+ * arena for the CAPACITY it allocated (stp_binning_capacity(binning_bytes) >= R), so the backward pass never needs R
+ * on the host.
  */
-int stp_backward(int P, int D, int M, int R,
+int stp_backward(int P, int D, int M, size_t binning_bytes,
                  const float* background, int width, int height,
                  const StpSettings* settings, const StpTileBand* band,
                  const float* means3D, const float* shs, const float* opacities,
@@ -138,7 +142,7 @@ int stp_backward(int P, int D, int M, int R,
  * stp_backward_preprocess then produces the dL_* rows of Gaussians [first, first+count) (first % 256 == 0), so the
  * all-reduce of one row range can run while the next range is computed (diff_gaussian_rasterization/_C.py,
  * sync_group=...).  stp_backward == stp_backward_render + stp_backward_preprocess(0, P). */
-int stp_backward_render(int P, int D, int M, int R,
+int stp_backward_render(int P, int D, int M, size_t binning_bytes,
                  const float* background, int width, int height,
                  const StpSettings* settings, const StpTileBand* band,
                  const float* means3D, const float* shs, const float* opacities,
@@ -152,7 +156,7 @@ int stp_backward_render(int P, int D, int M, int R,
                  float* dL_dmean2D, float* grad_accum, float* dL_dopacity, float* dL_dcolor,
                  float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                  int debug, void* stream);
-int stp_backward_preprocess(int P, int D, int M, int R,
+int stp_backward_preprocess(int P, int D, int M, size_t binning_bytes,
                  const float* background, int width, int height,
                  const StpSettings* settings, const StpTileBand* band,
                  const float* means3D, const float* shs, const float* opacities,
@@ -188,8 +192,8 @@ typedef struct StpGeometryView {
     uint32_t* tiles_touched; /* [P]   u32                                              */
 } StpGeometryView;
 typedef struct StpBinningView {
-    uint32_t* point_list;        /* [R] u32 sorted Gaussian ids                         */
-    uint64_t* point_list_keys;   /* [R] u64 sorted (tile<<32 | depth bits) keys          */
+    uint32_t* point_list;        /* [capacity] u32 sorted Gaussian ids, the first R valid  */
+    uint64_t* point_list_keys;   /* [capacity] u64 sorted (tile<<32 | depth bits) keys     */
 } StpBinningView;
 typedef struct StpImageView {
     float* final_T;       /* [W*H] f32 */
@@ -198,10 +202,13 @@ typedef struct StpImageView {
 } StpImageView;
 
 size_t stp_geometry_bytes(int P, int requires_cov3D_inv);
-size_t stp_binning_bytes(int R);
+/* arena size for `capacity` instances (rounded up to a multiple of 64) under the given settings (the depth-resorting
+ * modes add a 64-byte slab record per instance), and its exact inverse */
+size_t stp_binning_bytes(int capacity, const StpSettings* settings);
+int stp_binning_capacity(size_t binning_bytes, const StpSettings* settings);
 size_t stp_image_bytes(int width, int height, int blend_record_cap);
 int stp_view_geometry(char* geom_buffer, int P, int requires_cov3D_inv, StpGeometryView* out);
-int stp_view_binning(char* binning_buffer, int R, StpBinningView* out);
+int stp_view_binning(char* binning_buffer, int capacity, StpBinningView* out);
 int stp_view_image(char* image_buffer, int width, int height, StpImageView* out);
 /* SortSettings::requiresDepthAlongRay, rasterizer.h:66-71 */
 int stp_requires_cov3D_inv(const StpSettings* settings);

@@ -5,7 +5,9 @@
 // Everything is enqueued on the caller's stream; the only host<->device synchronisation is the
 // read-back of num_rendered that sizes the binning arena (the reference blocks in the same place,
 // rasterizer_impl.cu:317).
+#include <atomic>
 #include <cstdio>
+#include <mutex>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -21,9 +23,45 @@ thread_local std::string g_error;
 thread_local long long g_launches = 0;  // hand-written kernels launched by this thread (stp_kernel_launches)
 thread_local std::vector<std::pair<const char*, float>> g_timings;
 
+// Device-raised error flags that no read-back of the regular pipeline covers (the tile sort detecting that the
+// preprocess histogram and the duplicate kernel's emission disagree): one page of mapped pinned host memory, written by
+// the kernels with plain system-scope stores only when something is wrong, inspected by the host at the start of the
+// next call (and at the end of the same call with debug&1).  flags[0]: binning mismatch.
+uint32_t* host_error_flags() {
+    static uint32_t* flags = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 256, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
+            std::memset(p, 0, 256);
+            flags = static_cast<uint32_t*>(p);
+        } else {
+            (void)cudaGetLastError();
+        }
+    });
+    return flags;
+}
+
+// high-water mark of num_rendered per device: sizes the speculative binning-arena request
+constexpr int kMaxDevices = 64;
+std::atomic<uint32_t> g_last_R[kMaxDevices];
+
 int fail(int code, const std::string& msg) {
     g_error = msg;
     return code;
+}
+// sticky device-raised flags: reported (once) by the first call that sees them
+int report_device_flags() {
+    uint32_t* flags = host_error_flags();
+    if (flags == nullptr) return 0;
+    volatile uint32_t* v = flags;
+    if (v[0] != 0u) {
+        v[0] = 0u;
+        return fail(STP_ERR_CUDA, "tile binning: the per-tile instance histogram and the emitted instances disagree "
+                                  "(flag raised by a tile-sort kernel of this or an earlier call); the rendered output of "
+                                  "that call is invalid");
+    }
+    return 0;
 }
 int cuda_fail(cudaError_t e, const char* where) {
     g_error = std::string("CUDA error in ") + where + ": " + cudaGetErrorString(e);
@@ -226,7 +264,18 @@ int stp_requires_cov3D_inv(const StpSettings* s) {
 }
 
 size_t stp_geometry_bytes(int P, int inv) { return required<GeometryState>((size_t)P, inv != 0); }
-size_t stp_binning_bytes(int R) { return required<BinningState>((size_t)R); }
+size_t stp_binning_bytes(int capacity, const StpSettings* settings) {
+    const bool slab = settings != nullptr && settings->sort_mode != STP_SORT_GLOBAL;
+    return required<BinningState>((size_t)(capacity > 0 ? capacity : 0), slab);
+}
+// inverse of stp_binning_bytes: capacities are multiples of 64 instances, so every sub-array is a whole number of 256-byte
+// lines and the arena size is an exact linear function of the capacity
+int stp_binning_capacity(size_t bytes, const StpSettings* settings) {
+    const bool slab = settings != nullptr && settings->sort_mode != STP_SORT_GLOBAL;
+    const size_t fixed = required<BinningState>((size_t)0, slab);
+    if (bytes <= fixed) return 0;
+    return (int)((bytes - fixed) / (BinningState::bytes_per_instance(slab) * kBinningGranule) * kBinningGranule);
+}
 size_t stp_image_bytes(int W, int H, int rec_cap) {
     return required<ImageState>((size_t)W * H, (size_t)((W + 15) / 16) * ((H + 15) / 16), rec_cap > 0 ? rec_cap : 0);
 }
@@ -246,10 +295,10 @@ int stp_view_geometry(char* buf, int P, int inv, StpGeometryView* out) {
     out->tiles_touched = g.tiles_touched;
     return STP_OK;
 }
-int stp_view_binning(char* buf, int R, StpBinningView* out) {
+int stp_view_binning(char* buf, int capacity, StpBinningView* out) {
     if (buf == nullptr || out == nullptr) return fail(STP_ERR_INVALID_ARGUMENT, "null argument");
     char* p = buf;
-    BinningState b = BinningState::from_chunk(p, (size_t)R);
+    BinningState b = BinningState::from_chunk(p, (size_t)capacity, false);  // the index buffers come first
     out->point_list = b.point_list;
     out->point_list_keys = b.keys;
     return STP_OK;
@@ -285,6 +334,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     std::string err;
     if (!convert_settings(settings, s, err, false)) return fail(STP_ERR_UNSUPPORTED, err);
     if (P <= 0) return STP_OK;  // rasterize_points.cu:93
+    if (int rc = report_device_flags()) return rc;
     if (!geom_alloc || !binning_alloc || !image_alloc) return fail(STP_ERR_INVALID_ARGUMENT, "allocator callbacks required");
     if (shs == nullptr && colors_precomp == nullptr)
         return fail(STP_ERR_INVALID_ARGUMENT, "For non-RGB, provide precomputed Gaussian colors!");
@@ -297,8 +347,16 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
                          tan_fovy);
     const int tiles = f.grid_x * f.grid_y;
     const bool inv = s.requires_inv();
-    if (s.rec_cap > 0 && (double)tiles * 256.0 * (double)s.rec_cap >= 4294967296.0)
-        return fail(STP_ERR_INVALID_ARGUMENT, "blend_record_cap too large for this image (log is indexed with 32 bits)");
+    if (s.rec_cap > 0 && (double)tiles * 256.0 * (double)s.rec_cap >= 4294967296.0) {
+        // the log is indexed with 32 bits: very large images get the largest capacity that still fits; where the log is
+        // only an optimisation (GLOBAL / HIER: the list-driven backward handles overflowing pixels, or everything) a
+        // uselessly small one is dropped instead.  The backward pass re-derives the capacity from the arena size.
+        const int fit = (int)(4294967295.0 / ((double)tiles * 256.0));
+        const bool needed = s.sort_mode == STP_SORT_PPX_FULL || s.render_depth;
+        s.rec_cap = (fit >= 16 || needed) ? fit : 0;
+        if (needed && s.rec_cap <= 0)
+            return fail(STP_ERR_INVALID_ARGUMENT, "image too large for the blend log (indexed with 32 bits)");
+    }
     StageTimer timer((debug & 2) != 0, stream);
 
     char* gp = geom_alloc(geom_user, required<GeometryState>((size_t)P, inv));
@@ -325,26 +383,38 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     timer.mark("Preprocess");
 
     // The binning arena is sized by R, which is only known after the preprocess kernel.  While that kernel runs, the
-    // arena is requested speculatively for 1.25x the previous call's R (the allocation callback goes through the
-    // caller's allocator, tens of microseconds); the carve-up below uses the exact R, so a generous buffer changes
-    // nothing, and a too small one is simply requested again.
-    static thread_local uint32_t last_R = 0;
-    const size_t guess = last_R ? (size_t)last_R + last_R / 4 + 4096 : 0;
-    char* bp = guess ? binning_alloc(binning_user, required<BinningState>(guess)) : nullptr;
+    // arena is requested speculatively for 1.25x the largest R this device has seen (the allocation callback goes
+    // through the caller's allocator, tens of microseconds).  The arena is carved for the CAPACITY that was allocated
+    // (stp_binning_capacity of its size -- what the backward pass re-derives), so a generous buffer changes nothing,
+    // and a too small one is simply requested again.
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::atomic<uint32_t>& last_R = g_last_R[dev >= 0 && dev < kMaxDevices ? dev : 0];
+    const uint32_t seen = last_R.load(std::memory_order_relaxed);
+    const bool slab = s.uses_slab();
+    size_t cap = seen ? binning_round_cap((size_t)seen + seen / 4 + 4096) : 0;
+    char* bp = cap ? binning_alloc(binning_user, required<BinningState>(cap, slab)) : nullptr;
 
     uint32_t R = 0;
     {
-        cudaError_t e = cudaMemcpyAsync(&R, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+        uint32_t rf[2] = {0, 0};  // counters[1] = R, counters[2] = error flags raised by the preprocess kernel
+        cudaError_t e = cudaMemcpyAsync(rf, g.counters + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess) return cuda_fail(e, "num_rendered read-back");
         e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return cuda_fail(e, "num_rendered read-back");
+        R = rf[0];
+        if (rf[1] & 1u)  // the reference traps here (auxiliary.h:226-233)
+            return fail(STP_ERR_INVALID_ARGUMENT, "Point is filtered although prefiltered is set. This shouldn't happen!");
     }
     if (num_rendered_out) *num_rendered_out = (int)R;
-    last_R = R;
+    if (R > seen) last_R.store(R, std::memory_order_relaxed);
 
-    if (bp == nullptr || (size_t)R > guess) bp = binning_alloc(binning_user, required<BinningState>((size_t)R));
+    if (bp == nullptr || (size_t)R > cap) {
+        cap = binning_round_cap((size_t)R);
+        bp = binning_alloc(binning_user, required<BinningState>(cap, slab));
+    }
     if (!bp) return fail(STP_ERR_ALLOC, "binning arena allocation failed");
-    BinningState b = BinningState::from_chunk(bp, (size_t)R);
+    BinningState b = BinningState::from_chunk(bp, cap, slab);
 
     if (R > 0) {
         STP_CUDA(launch_duplicate(P, f, s, g, radii, img, b, (size_t)R, stream), "duplicate");
@@ -352,7 +422,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     }
     timer.mark("Duplicate");
     if (R > 0) {
-        STP_CUDA(launch_tile_sort(f, g, img, b, stream), "tile sort");
+        STP_CUDA(launch_tile_sort(f, g, img, b, host_error_flags(), stream), "tile sort");
         g_launches += sort_kernel_launches();
     }
     timer.mark("Sort");
@@ -360,6 +430,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     RenderArgs ra;
     ra.ranges = img.ranges;
     ra.point_list = b.point_list;
+    ra.slab = b.slab;
     ra.means2D = g.means2D;
     ra.conic_opacity = g.conic_opacity;
     ra.cov3D_inv = g.cov3D_inv;
@@ -397,6 +468,9 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
         timer.mark("DepthVisualisation");
     }
     timer.finish();
+    if (debug & 1) {  // every stage has been synchronised: flags raised by this very call are visible
+        if (int rc = report_device_flags()) return rc;
+    }
     return STP_OK;
 }
 
@@ -404,7 +478,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
 
 namespace {
 // which = 1: render backward only; 2: preprocess backward only (Gaussians [first, first+count)); 3: both
-int backward_impl(int which, int first, int count, int P, int D, int M, int R, const float* background, int width,
+int backward_impl(int which, int first, int count, int P, int D, int M, size_t binning_bytes, const float* background, int width,
                   int height, const StpSettings* settings, const StpTileBand* band, const float* means3D, const float* shs,
                   const float* opacities, const float* colors_precomp, const float* scales, float scale_modifier,
                   const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
@@ -432,7 +506,8 @@ int backward_impl(int which, int first, int count, int P, int D, int M, int R, c
     char* gp = geom_buffer;
     GeometryState g = GeometryState::from_chunk(gp, (size_t)P, inv);
     char* bp = binning_buffer;
-    BinningState b = BinningState::from_chunk(bp, (size_t)R);
+    const size_t R = (size_t)stp_binning_capacity(binning_bytes, settings);  // capacity the forward pass carved the arena for
+    BinningState b = BinningState::from_chunk(bp, R, s.uses_slab());
     char* ip = image_buffer;
     ImageState img = ImageState::from_chunk(ip, (size_t)width * height, (size_t)tiles, s.rec_cap);
 
@@ -440,6 +515,7 @@ int backward_impl(int which, int first, int count, int P, int D, int M, int R, c
         RenderBwdArgs ra;
         ra.ranges = img.ranges;
         ra.point_list = b.point_list;
+        ra.slab = b.slab;
         ra.means2D = g.means2D;
         ra.conic_opacity = g.conic_opacity;
         ra.cov3D_inv = g.cov3D_inv;
@@ -500,7 +576,8 @@ int backward_impl(int which, int first, int count, int P, int D, int M, int R, c
 extern "C" {
 
 #define STP_BWD_PARAMS                                                                                                       \
-    int P, int D, int M, int R, const float *background, int width, int height, const StpSettings *settings,                 \
+    int P, int D, int M, size_t binning_bytes, const float *background, int width, int height,                              \
+        const StpSettings *settings,                                                                                        \
         const StpTileBand *band, const float *means3D, const float *shs, const float *opacities,                             \
         const float *colors_precomp, const float *scales, float scale_modifier, const float *rotations,                      \
         const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, const float *inv_viewprojmatrix,       \
@@ -509,7 +586,7 @@ extern "C" {
         float *grad_accum, float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D, float *dL_dcov3D, float *dL_dsh,         \
         float *dL_dscale, float *dL_drot, int debug, void *stream
 #define STP_BWD_ARGS                                                                                                         \
-    P, D, M, R, background, width, height, settings, band, means3D, shs, opacities, colors_precomp, scales, scale_modifier, \
+    P, D, M, binning_bytes, background, width, height, settings, band, means3D, shs, opacities, colors_precomp, scales, scale_modifier, \
         rotations, cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, cam_pos, tan_fovx, tan_fovy, pixel_colors,    \
         radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dmean2D, grad_accum, dL_dopacity, dL_dcolor,          \
         dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream

@@ -19,6 +19,7 @@
 // HBM traffic: 8 B written + 8 B read + 12 B written per instance.
 #include "stp_kernels.cuh"
 #include "stp_sort.cuh"
+#include "stp_slab.cuh"
 
 namespace stp {
 
@@ -297,13 +298,28 @@ __device__ __forceinline__ int pow2_at_least(int n) {
     return np;
 }
 
-struct EmitSorted {  // final outputs: the reference's point_list_keys / point_list
+// what the sort epilogue needs to write the tile's slab (stp_slab.cuh); slab == nullptr: index buffers only
+struct SlabSource {
+    float4* slab;
+    const float2* means2D;
+    const float4* conic_opacity;
+    const float4* cov3D_inv;
+};
+struct EmitSorted {  // final outputs: the reference's point_list_keys / point_list, and the slab record of the instance
     uint64_t* keys;
     uint32_t* point_list;
     uint64_t tile_hi;
+    uint32_t first;  // absolute list position of the tile's first instance
+    SlabSource src;
     __device__ __forceinline__ void operator()(int i, uint64_t v) const {
         keys[i] = tile_hi | (v >> 32);
-        point_list[i] = (uint32_t)v;
+        const uint32_t id = (uint32_t)v;
+        point_list[i] = id;
+        if (src.slab != nullptr) {
+            const float4* const inv = src.cov3D_inv + 3 * (size_t)id;
+            slab_store(src.slab, first + (uint32_t)i, (int)id, __ldg(src.means2D + id), __ldg(src.conic_opacity + id),
+                       __ldg(inv), __ldg(inv + 1), __ldg(inv + 2));
+        }
     }
 };
 struct EmitRaw {  // sorted chunk back to the bucket (input of the merge passes)
@@ -311,19 +327,30 @@ struct EmitRaw {  // sorted chunk back to the bucket (input of the merge passes)
     __device__ __forceinline__ void operator()(int i, uint64_t v) const { dst[i] = v; }
 };
 
+// the preprocess histogram and the duplicate kernel's emission disagree for this tile (a bug, or corrupted inputs):
+// the bucket holds stale records.  Raised in the geometry arena (counters[2], bit 2) and in the library's mapped host
+// word, which the host inspects at its next entry (api.cu: host_error_flags)
+__device__ __forceinline__ void flag_binning_mismatch(uint32_t* counters, uint32_t* host_flags) {
+    atomicOr(counters + 2, 2u);
+    if (host_flags != nullptr) {
+        *reinterpret_cast<volatile uint32_t*>(host_flags) = 1u;
+        __threadfence_system();
+    }
+}
+
 // one CTA per tile, tiles of at most kSmallCap instances
 __global__ void __launch_bounds__(256)
 tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cursor,
                        const uint64_t* __restrict__ bucket, uint64_t* __restrict__ keys, uint32_t* __restrict__ point_list,
-                       uint32_t* __restrict__ counters) {
+                       uint32_t* __restrict__ counters, SlabSource src, uint32_t* host_flags) {
     __shared__ uint64_t s[kSmallCap];
     const uint32_t tile = blockIdx.x;
     const uint2 r = ranges[tile];
     const int n = (int)(r.y - r.x), tid = threadIdx.x;
     if (n == 0 || n > kSmallCap) return;
-    if (tid == 0 && cursor[tile] != r.y) atomicOr(counters + 2, 2u);  // histogram and emission disagree
+    if (tid == 0 && cursor[tile] != r.y) flag_binning_mismatch(counters, host_flags);
     const int np = pow2_at_least(n);
-    const EmitSorted emit{keys + r.x, point_list + r.x, (uint64_t)tile << 32};
+    const EmitSorted emit{keys + r.x, point_list + r.x, (uint64_t)tile << 32, r.x, src};
     if (np <= 512)
         bitonic_sort_tile<2, 256>(bucket + r.x, n, np, s, tid, emit);
     else if (np == 1024)
@@ -355,7 +382,7 @@ __global__ void __launch_bounds__(kLargeThreads)
 tile_sort_large_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ cursor,
                        const uint32_t* __restrict__ large_tiles, uint64_t* bucket, uint64_t* scratch, uint64_t* keys,
                        uint32_t* point_list,
-                       uint32_t* __restrict__ counters) {
+                       uint32_t* __restrict__ counters, SlabSource src, uint32_t* host_flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
     const int tid = threadIdx.x;
@@ -364,10 +391,10 @@ tile_sort_large_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         const uint32_t tile = large_tiles[w];
         const uint2 r = ranges[tile];
         const int n = (int)(r.y - r.x);
-        if (tid == 0 && cursor[tile] != r.y) atomicOr(counters + 2, 2u);
+        if (tid == 0 && cursor[tile] != r.y) flag_binning_mismatch(counters, host_flags);
         if (n <= kLargeCap) {
             const int np = pow2_at_least(n);
-            const EmitSorted emit{keys + r.x, point_list + r.x, (uint64_t)tile << 32};
+            const EmitSorted emit{keys + r.x, point_list + r.x, (uint64_t)tile << 32, r.x, src};
             if (np <= 4096)
                 bitonic_sort_tile<4, kLargeThreads>(bucket + r.x, n, np, s, tid, emit);
             else if (np == 8192)
@@ -402,7 +429,7 @@ tile_sort_large_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         }
         __threadfence_block();
         __syncthreads();
-        const EmitSorted emit{keys + r.x, point_list + r.x, (uint64_t)tile << 32};
+        const EmitSorted emit{keys + r.x, point_list + r.x, (uint64_t)tile << 32, r.x, src};
         for (int i = tid; i < n; i += kLargeThreads) emit(i, a[i]);
         __syncthreads();
     }
@@ -442,19 +469,19 @@ cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const Image
 int sort_kernel_launches() { return 2; }
 
 cudaError_t launch_tile_sort(const Frame& f, const GeometryState& g, const ImageState& img, const BinningState& b,
-                             cudaStream_t stream) {
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(tile_sort_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(kLargeCap * sizeof(uint64_t)));
-    }
+                             uint32_t* host_flags, cudaStream_t stream) {
+    // per call, not cached in a process-wide static: both the attribute and the SM count belong to the CURRENT device
+    // (a process may drive several GPUs); the two driver calls cost about a microsecond
+    int dev = 0, sm_count = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(tile_sort_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(kLargeCap * sizeof(uint64_t)));
+    const SlabSource src{b.slab, g.means2D, g.conic_opacity, g.cov3D_inv};
     tile_sort_small_kernel<<<f.grid_x * f.grid_y, 256, 0, stream>>>(img.ranges, img.tile_cursor, b.bucket, b.keys,
-                                                                    b.point_list, g.counters);
+                                                                    b.point_list, g.counters, src, host_flags);
     tile_sort_large_kernel<<<sm_count, kLargeThreads, kLargeCap * sizeof(uint64_t), stream>>>(
-        img.ranges, img.tile_cursor, img.large_tiles, b.bucket, b.scratch, b.keys, b.point_list, g.counters);
+        img.ranges, img.tile_cursor, img.large_tiles, b.bucket, b.scratch, b.keys, b.point_list, g.counters, src, host_flags);
     return cudaGetLastError();
 }
 

@@ -285,8 +285,9 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
         const F3 dir_orig = {mean.x - f.cam_pos[0], mean.y - f.cam_pos[1], mean.z - f.cam_pos[2]};
         const float len = sqrtf(dot(dir_orig, dir_orig));
         const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-        const float* __restrict__ shp = row ? row : a.shs + (size_t)idx * a.M * 3;
-        float* __restrict__ dsh = row ? row : a.dL_dsh + (size_t)idx * a.M * 3;
+        // no __restrict__: in the staged path both point at the same shared-memory row, which is rewritten in place
+        const float* shp = row ? row : a.shs + (size_t)idx * a.M * 3;
+        float* dsh = row ? row : a.dL_dsh + (size_t)idx * a.M * 3;
         const int D = a.D;
         auto sh = [&](int k) { return F3{shp[3 * k], shp[3 * k + 1], shp[3 * k + 2]}; };
         F3 dRGB = {acc1.z, acc1.w, acc_cb};
@@ -339,9 +340,9 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
             }
         }
         {
-            // direct path: only the active coefficients are written (the rest stays at the caller's zeros);
-            // staged path: the whole row is rewritten
-            const int ncoef = row ? a.M : min(a.M, (D + 1) * (D + 1));
+            // every one of the M coefficients is written on both paths (wk is zero beyond the active degree): dL_dsh is a
+            // pure output that the caller does not zero-fill
+            const int ncoef = a.M;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 if (k < ncoef) {

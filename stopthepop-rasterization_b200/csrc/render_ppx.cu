@@ -18,6 +18,7 @@
 // for lists <= 1024 entries, like the reference.
 #include "stp_kernels.cuh"
 #include "stp_sort.cuh"
+#include "stp_slab.cuh"
 
 namespace stp {
 
@@ -287,13 +288,21 @@ __device__ __forceinline__ void bitonic_sort_1024(float (&k)[32], int (&v)[32], 
 // over the keys.  Exact key ties, whose order in the reference depends on the history of its window, are not
 // resolved here: a pixel with a tie among its survivors, a tie of its last contributor with any entry, or more
 // than kFastSurv survivors is marked (n_contrib = ~0) and left to render_full_kernel below.
+//
+// Data movement: the tile's slab (64-byte records in list order, written by the tile-sort epilogue, stp_slab.cuh) is
+// pulled into shared memory ONCE per tile with a single bulk-async copy (TMA, completion on an mbarrier) and then
+// serves all 256 pixels: every (pixel, entry) evaluation is four conflict-free 128-bit shared-memory loads instead of
+// 76 bytes of global gathers through the instance's Gaussian id (the reference re-fetches per pixel,
+// resorted_render.cuh:598-600).  One 512-thread CTA per SM: 16 warps, each owning one pixel row of the tile.
 constexpr int kFastSurv = 256;
+constexpr int kFastWarps = 16;
+constexpr int kFastThreads = kFastWarps * 32;
 constexpr uint32_t kSlowMark = 0xFFFFFFFFu;
 struct FullFastShared {
-    uint32_t key[8][1024];                 // order-preserving integer image of every entry's ray depth, per warp
-    unsigned long long surv[8][kFastSurv]; // (key << 32 | slot) of the alpha-test survivors
-    float alpha[8][kFastSurv];
-    int id[8][kFastSurv];
+    float4 slab[1024 * kSlabChunks];                  // 64 KB, destination of the bulk copy
+    uint32_t key[kFastWarps][1024];                   // order-preserving integer image of every entry's ray depth, per warp
+    unsigned long long surv[kFastWarps][kFastSurv];   // (key << 32 | list position) of the alpha-test survivors
+    uint64_t bar;
 };
 
 __device__ __forceinline__ uint32_t sortable_bits(float x) {  // monotone float -> uint32 (-0 folded into +0)
@@ -301,11 +310,27 @@ __device__ __forceinline__ uint32_t sortable_bits(float x) {  // monotone float 
     return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
 }
 
-// sorts the S survivors of one pixel (E*32 >= S) and blends them front to back; returns false if a key tie was found
+// alpha of slab record idx at the pixel, the forward spelling of resorted_render.cuh:165-173; false = rejected
+__device__ __forceinline__ bool slab_alpha(const float4* __restrict__ slab, int idx, uint32_t first, float pxf, float pyf,
+                                           float& alpha, int& id) {
+    float4 c0, c1;
+    slab_load_head(slab + 4 * idx, first + (uint32_t)idx, c0, c1);
+    id = __float_as_int(c1.z);
+    const float dx = fsub(c0.x, pxf), dy = fsub(c0.y, pyf);
+    const float pw = opacity_factor(dx, dy, c0.z, c0.w, c1.x);
+    if (pw < 0.0f) return false;
+    alpha = fminf(0.99f, fmul(c1.y, expf(-pw)));
+    return !(alpha < kAlphaThreshold);
+}
+
+// sorts the S survivors of one pixel (E*32 >= S) and blends them front to back; returns false if a key tie was found.
+// The transmittance chain is sequential (it decides where the pixel stops, and with it n_contrib, final_T and the blend
+// log, all bit-exact); the colour sum of a group of 32 blends is a warp tree reduction.
 template <int E>
-__device__ __forceinline__ bool full_fast_sort_blend(const FullFastShared& sh, int warp, int lane, int S, const RenderArgs& a,
-                                                     bool logging, uint32_t rec_first, float& T, float& C0, float& C1,
-                                                     float& C2, uint32_t& last_key, bool& have_last, uint32_t& nrec) {
+__device__ __forceinline__ bool full_fast_sort_blend(const FullFastShared& sh, int warp, int lane, int S, uint32_t first,
+                                                     float pxf, float pyf, const RenderArgs& a, bool logging,
+                                                     uint32_t rec_first, float& T, float& C0, float& C1, float& C2,
+                                                     uint32_t& last_key, bool& have_last, uint32_t& nrec) {
     uint64_t v[E];
 #pragma unroll
     for (int r = 0; r < E; ++r) {
@@ -333,47 +358,55 @@ __device__ __forceinline__ bool full_fast_sort_blend(const FullFastShared& sh, i
     for (int r = 0; r < E; ++r) {
         if (done || r * 32 >= S) break;
         const int e = r * 32 + lane;
-        const bool valid = e < S;
-        const uint32_t slot = (uint32_t)v[r] & (kFastSurv - 1);
         const uint32_t mykey = (uint32_t)(v[r] >> 32);
-        float alpha = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        float alpha = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
         int id = -1;
-        if (valid) {
-            alpha = sh.alpha[warp][slot];
-            id = sh.id[warp][slot];
-            c0 = __ldg(a.colors + 3 * id + 0);
-            c1 = __ldg(a.colors + 3 * id + 1);
-            c2 = __ldg(a.colors + 3 * id + 2);
+        if (e < S) {
+            slab_alpha(sh.slab, (int)((uint32_t)v[r] & 1023u), first, pxf, pyf, alpha, id);  // passed before: same bits
+            w0 = fmul(__ldg(a.colors + 3 * id + 0), alpha);
+            w1 = fmul(__ldg(a.colors + 3 * id + 1), alpha);
+            w2 = fmul(__ldg(a.colors + 3 * id + 2), alpha);
         }
         const int cnt = min(32, S - r * 32);
+        float myT = 0.f;
+        int stop = cnt;
         for (int l = 0; l < cnt; ++l) {
             const float al = __shfl_sync(0xffffffffu, alpha, l);
             const float test_T = fmul(T, fsub(1.0f, al));
             if (test_T < kTThreshold) {
                 done = true;
+                stop = l;
                 break;
             }
-            const float b0 = __shfl_sync(0xffffffffu, c0, l), b1 = __shfl_sync(0xffffffffu, c1, l),
-                        b2 = __shfl_sync(0xffffffffu, c2, l);
-            C0 = ffma(fmul(b0, al), T, C0);
-            C1 = ffma(fmul(b1, al), T, C1);
-            C2 = ffma(fmul(b2, al), T, C2);
+            myT = (lane == l) ? T : myT;
             T = test_T;
-            last_key = __shfl_sync(0xffffffffu, mykey, l);
+        }
+        if (stop > 0) {
+            float t0 = w0 * myT, t1 = w1 * myT, t2 = w2 * myT;  // lanes >= stop hold myT = 0
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+                t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+                t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+            }
+            C0 += t0;
+            C1 += t1;
+            C2 += t2;
+            last_key = __shfl_sync(0xffffffffu, mykey, stop - 1);
             have_last = true;
             if (logging) {
-                if (lane == l && nrec < (uint32_t)a.rec_cap)
-                    __stcs(a.blend_rec + rec_first + nrec * 256u, make_uint2((uint32_t)id, __float_as_uint(al)));
-                ++nrec;
+                if (lane < stop && nrec + (uint32_t)lane < (uint32_t)a.rec_cap)
+                    __stcs(a.blend_rec + rec_first + (nrec + (uint32_t)lane) * 256u, make_uint2((uint32_t)id, __float_as_uint(alpha)));
+                nrec += (uint32_t)stop;
             }
         }
     }
     return true;
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kFastThreads, 1)
 render_full_fast_kernel(Frame f, RenderArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_full[];
+    extern __shared__ __align__(128) unsigned char smem_full[];
     FullFastShared& sh = *reinterpret_cast<FullFastShared*>(smem_full);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
@@ -382,13 +415,26 @@ render_full_fast_kernel(Frame f, RenderArgs a) {
     const uint2 range = a.ranges[tile_lin];
     const int n = (int)(range.y - range.x);
     if (n > 1024) return;  // render_full_kernel emulates the sliding window for long lists
+    // the tile's slab: one bulk-async copy, everybody waits on its mbarrier
+    if (tid == 0) {
+        mbar_init(&sh.bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0 && n > 0) {
+        mbar_expect_tx(&sh.bar, (uint32_t)n * kSlabRecordBytes);
+        bulk_g2s(sh.slab, a.slab + (size_t)kSlabChunks * range.x, (uint32_t)n * kSlabRecordBytes, &sh.bar);
+    }
     const RayCam cam = make_raycam(f.inv_viewproj, f.cam_pos, f.W, f.H);
     const bool logging = a.blend_rec != nullptr;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t py = tile_y * 16 + warp;
+    if (n > 0) mbar_wait(&sh.bar, 0);
+    if (!(py < (uint32_t)f.H)) return;  // warp-uniform; nothing is pending any more
 
-    for (int pi = 0; pi < 32; ++pi) {
-        const uint32_t px = tile_x * 16 + (pi & 15), py = tile_y * 16 + warp * 2 + (pi >> 4);
-        if (!(px < (uint32_t)f.W && py < (uint32_t)f.H)) continue;  // warp-uniform
+    for (int pi = 0; pi < 16; ++pi) {
+        const uint32_t px = tile_x * 16 + pi;
+        if (!(px < (uint32_t)f.W)) break;  // warp-uniform
         const uint32_t pix_id = (uint32_t)f.W * py + px;
         const float pxf = (float)px, pyf = (float)py;
         const Vec3 ray = view_ray(cam, pxf, pyf);
@@ -398,43 +444,37 @@ render_full_fast_kernel(Frame f, RenderArgs a) {
             const int idx = base + lane;
             bool accept = false;
             uint32_t skey = 0xFFFFFFFFu;
-            float alpha = 0.f;
-            int id = -1;
             if (idx < n) {
-                id = (int)__ldg(a.point_list + range.x + idx);
-                float ic[6], ux, uy, uz;
-                load_inv(a.cov3D_inv, id, ic, ux, uy, uz);
-                skey = sortable_bits(depth_along_ray(ic, ux, uy, uz, ray));
+                const uint32_t j = range.x + (uint32_t)idx;
+                float4 c0, c1, c2, c3;
+                slab_load_head(sh.slab + 4 * idx, j, c0, c1);
+                slab_load_tail(sh.slab + 4 * idx, j, c2, c3);
+                const float ic[6] = {c1.w, c2.x, c2.y, c2.z, c2.w, c3.x};
+                skey = sortable_bits(depth_along_ray(ic, c3.y, c3.z, c3.w, ray));
                 sh.key[warp][idx] = skey;
-                const float2 xy = __ldg(a.means2D + id);
-                const float4 co = __ldg(a.conic_opacity + id);
-                const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
-                const float pw = opacity_factor(dx, dy, co.x, co.y, co.z);
-                if (!(pw < 0.0f)) {
-                    alpha = fminf(0.99f, fmul(co.w, expf(-pw)));
-                    accept = !(alpha < kAlphaThreshold);
-                }
+                const float dx = fsub(c0.x, pxf), dy = fsub(c0.y, pyf);
+                const float pw = opacity_factor(dx, dy, c0.z, c0.w, c1.x);
+                if (!(pw < 0.0f)) accept = !(fminf(0.99f, fmul(c1.y, expf(-pw))) < kAlphaThreshold);
             }
             const uint32_t m = __ballot_sync(0xffffffffu, accept);
             const int slot = S + __popc(m & lt_mask);
-            if (accept && slot < kFastSurv) {
-                sh.surv[warp][slot] = ((unsigned long long)skey << 32) | (unsigned long long)slot;
-                sh.alpha[warp][slot] = alpha;
-                sh.id[warp][slot] = id;
-            }
+            if (accept && slot < kFastSurv)
+                sh.surv[warp][slot] = ((unsigned long long)skey << 32) | (unsigned long long)idx;
             S += __popc(m);
         }
         __syncwarp();
         float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
         uint32_t last_key = 0, nrec = 0;
         bool have_last = false;
-        const uint32_t rec_first = tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)(warp * 32 + pi);
+        const uint32_t rec_first = tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)(warp * 16 + pi);
         bool ok = S <= kFastSurv;
         if (ok) {
-            if (S <= 32) ok = full_fast_sort_blend<1>(sh, warp, lane, S, a, logging, rec_first, T, C0, C1, C2, last_key, have_last, nrec);
-            else if (S <= 64) ok = full_fast_sort_blend<2>(sh, warp, lane, S, a, logging, rec_first, T, C0, C1, C2, last_key, have_last, nrec);
-            else if (S <= 128) ok = full_fast_sort_blend<4>(sh, warp, lane, S, a, logging, rec_first, T, C0, C1, C2, last_key, have_last, nrec);
-            else ok = full_fast_sort_blend<8>(sh, warp, lane, S, a, logging, rec_first, T, C0, C1, C2, last_key, have_last, nrec);
+#define STP_FAST(E_) full_fast_sort_blend<E_>(sh, warp, lane, S, range.x, pxf, pyf, a, logging, rec_first, T, C0, C1, C2, last_key, have_last, nrec)
+            if (S <= 32) ok = STP_FAST(1);
+            else if (S <= 64) ok = STP_FAST(2);
+            else if (S <= 128) ok = STP_FAST(4);
+            else ok = STP_FAST(8);
+#undef STP_FAST
         }
         uint32_t last_contributor = 0;
         if (ok && have_last) {
@@ -498,9 +538,8 @@ render_full_kernel(Frame f, RenderArgs a) {
             float key = kFltMax;
             int payload = -1;
             if (idx < n) {
-                const int id = (int)__ldg(a.point_list + range.x + idx);
                 float ic[6], ux, uy, uz;
-                load_inv(a.cov3D_inv, id, ic, ux, uy, uz);
+                slab_ldg_inv(a.slab, range.x + (uint32_t)idx, ic, ux, uy, uz);
                 key = depth_along_ray(ic, ux, uy, uz, ray);
                 payload = (idx << 10) | ord;
             }
@@ -540,14 +579,14 @@ render_full_kernel(Frame f, RenderArgs a) {
                     bool accept = false;
                     int my_id = -1;
                     if (e < lim && v[r] >= 0) {
-                        const int id = (int)__ldg(a.point_list + range.x + (v[r] >> 10));
+                        float4 h0, h1;
+                        slab_ldg_head(a.slab, range.x + (uint32_t)(v[r] >> 10), h0, h1);
+                        const int id = __float_as_int(h1.z);
                         my_id = id;
-                        const float2 xy = __ldg(a.means2D + id);
-                        const float4 co = __ldg(a.conic_opacity + id);
-                        const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
-                        const float pw = opacity_factor(dx, dy, co.x, co.y, co.z);
+                        const float dx = fsub(h0.x, pxf), dy = fsub(h0.y, pyf);
+                        const float pw = opacity_factor(dx, dy, h0.z, h0.w, h1.x);
                         if (!(pw < 0.0f)) {
-                            alpha = fminf(0.99f, fmul(co.w, expf(-pw)));
+                            alpha = fminf(0.99f, fmul(h1.y, expf(-pw)));
                             accept = !(alpha < kAlphaThreshold);
                         }
                         if (accept) {
@@ -635,12 +674,9 @@ cudaError_t launch_render_kbuffer_bwd(const Frame& f, const Settings& s, const R
 cudaError_t launch_render_full_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream) {
     dim3 grid(f.grid_x, f.row1 - f.row0, 1);
     if (grid.y == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(render_full_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullFastShared));
-        attr_set = true;
-    }
-    render_full_fast_kernel<<<grid, kBlock, sizeof(FullFastShared), stream>>>(f, a);
+    // per launch: the attribute belongs to the current device, a process may drive several GPUs
+    cudaFuncSetAttribute(render_full_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullFastShared));
+    render_full_fast_kernel<<<grid, kFastThreads, sizeof(FullFastShared), stream>>>(f, a);
     render_full_kernel<<<grid, kBlock, 0, stream>>>(f, a);
     return cudaGetLastError();
 }

@@ -23,6 +23,7 @@ struct PreprocessArgs {
 struct RenderArgs {
     const uint2* ranges;
     const uint32_t* point_list;
+    const float4* slab;   // per-tile slabs in list order (stp_slab.cuh), nullptr in GLOBAL mode
     const float2* means2D;
     const float4* conic_opacity;
     const float4* cov3D_inv;
@@ -40,6 +41,7 @@ struct RenderArgs {
 struct RenderBwdArgs {
     const uint2* ranges;
     const uint32_t* point_list;
+    const float4* slab;
     const float2* means2D;
     const float4* conic_opacity;
     const float4* cov3D_inv;
@@ -136,7 +138,7 @@ cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const Image
 cudaError_t launch_duplicate(int P, const Frame& f, const Settings& s, const GeometryState& g, const int* radii,
                              const ImageState& img, const BinningState& b, size_t cap, cudaStream_t stream);
 cudaError_t launch_tile_sort(const Frame& f, const GeometryState& g, const ImageState& img, const BinningState& b,
-                             cudaStream_t stream);
+                             uint32_t* host_flags, cudaStream_t stream);
 
 // render_global.cu
 cudaError_t launch_render_global_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream);

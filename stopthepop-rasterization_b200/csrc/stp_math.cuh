@@ -266,19 +266,5 @@ STP_DEV float per_tile_depth_key(const float* __restrict__ ic, float ux, float u
     return fmaxf(0.0f, ffma(num, rcp, 8.0f));
 }
 
-// getHigherMsb (rasterizer_impl.cu:37-52): number of tile-id bits that take part in the sort.
-static inline uint32_t higher_msb(uint32_t n) {
-    uint32_t msb = sizeof(n) * 4;
-    uint32_t step = msb;
-    while (step > 1) {
-        step /= 2;
-        if (n >> msb)
-            msb += step;
-        else
-            msb -= step;
-    }
-    if (n >> msb) msb++;
-    return msb;
-}
 
 }  // namespace stp

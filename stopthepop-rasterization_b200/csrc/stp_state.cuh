@@ -89,23 +89,33 @@ struct ImageState {
     }
 };
 
-// per-instance arena: 28 B/instance.  point_list / keys are the sorted outputs (the reference's
+// per-instance arena: 28 B/instance (+64 B with slabs).  point_list / keys are the sorted outputs (the reference's
 // point_list / point_list_keys, rasterizer_impl.h:57-67); bucket holds the unsorted
 // (depth bits << 32 | Gaussian index) records grouped by tile, scratch is the ping-pong buffer of the
-// global merge passes that only tiles longer than the in-smem capacity need.
+// global merge passes that only tiles longer than the in-smem capacity need; slab holds one 64-byte record per
+// instance in list order (stp_slab.cuh) for the render modes that evaluate depth along rays.
+// `cap` is the instance CAPACITY the arena was carved for (>= num_rendered); the backward pass re-derives it from the
+// arena size (binning_capacity), so it never needs num_rendered on the host.
+constexpr size_t kBinningGranule = 64;  // capacities are multiples of this: every sub-array is a whole number of 256-byte lines
+static inline size_t binning_round_cap(size_t n) { return (n + kBinningGranule - 1) / kBinningGranule * kBinningGranule; }
 struct BinningState {
     uint32_t* point_list;
     uint64_t* keys;
     uint64_t* bucket;
     uint64_t* scratch;
-    static BinningState from_chunk(char*& chunk, size_t R) {
+    float4* slab;  // nullptr unless requested
+    static BinningState from_chunk(char*& chunk, size_t cap, bool with_slab) {
         BinningState b;
-        obtain(chunk, b.point_list, R);
-        obtain(chunk, b.keys, R);
-        obtain(chunk, b.bucket, R);
-        obtain(chunk, b.scratch, R);
+        cap = binning_round_cap(cap);
+        obtain(chunk, b.point_list, cap);
+        obtain(chunk, b.keys, cap);
+        obtain(chunk, b.bucket, cap);
+        obtain(chunk, b.scratch, cap);
+        b.slab = nullptr;
+        if (with_slab) obtain(chunk, b.slab, cap * 4);
         return b;
     }
+    static size_t bytes_per_instance(bool with_slab) { return 4 + 8 + 8 + 8 + (with_slab ? 64 : 0); }
 };
 
 template <typename T, typename... A>
@@ -137,6 +147,7 @@ struct Settings {
     bool render_depth;  // DebugVisualization::Depth instead of the colour image
     bool per_tile_depth() const { return sort_order == 2 || sort_order == 3; }
     bool requires_inv() const { return sort_mode != 0 || per_tile_depth(); }
+    bool uses_slab() const { return sort_mode != 0; }  // HIER / PPX_FULL / PPX_KBUFFER render from per-tile slabs
 };
 
 }  // namespace stp

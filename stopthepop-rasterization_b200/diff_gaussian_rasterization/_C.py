@@ -62,7 +62,9 @@ _lib.stp_abi_version.restype = ctypes.c_int
 _lib.stp_geometry_bytes.restype = ctypes.c_size_t
 _lib.stp_geometry_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
 _lib.stp_binning_bytes.restype = ctypes.c_size_t
-_lib.stp_binning_bytes.argtypes = [ctypes.c_int]
+_lib.stp_binning_bytes.argtypes = [ctypes.c_int, ctypes.POINTER(StpSettings)]
+_lib.stp_binning_capacity.restype = ctypes.c_int
+_lib.stp_binning_capacity.argtypes = [ctypes.c_size_t, ctypes.POINTER(StpSettings)]
 _lib.stp_image_bytes.restype = ctypes.c_size_t
 _lib.stp_image_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
 _lib.stp_requires_cov3D_inv.argtypes = [ctypes.POINTER(StpSettings)]
@@ -86,7 +88,7 @@ _lib.stp_forward.argtypes = [
     _P, _P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_int)]  # out_color radii debug stream num_rendered
 _lib.stp_backward.restype = ctypes.c_int
 _lib.stp_backward.argtypes = [
-    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,  # P D M R
+    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,  # P D M binning_bytes
     _P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(StpSettings), ctypes.POINTER(StpTileBand),
     _P, _P, _P, _P, _P, ctypes.c_float, _P, _P,  # means3D shs opac colors scales mod rot cov3D
     _P, _P, _P, _P, ctypes.c_float, ctypes.c_float,  # view proj inv campos tanx tany
@@ -99,7 +101,7 @@ _lib.stp_backward_render.argtypes = list(_lib.stp_backward.argtypes)
 _lib.stp_backward_preprocess.restype = ctypes.c_int
 _lib.stp_backward_preprocess.argtypes = list(_lib.stp_backward.argtypes) + [ctypes.c_int, ctypes.c_int]
 
-if _lib.stp_abi_version() != 4:
+if _lib.stp_abi_version() != 5:
     raise ImportError("libstp_rasterizer.so ABI version mismatch")
 
 LIBRARY_PATH = _LIB_PATH
@@ -279,7 +281,10 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
          pixel_colors, dL_dout_color, sh, campos) = keep
         radii = radii.contiguous()
         band = ctypes.byref(StpTileBand(int(tile_band[0]), int(tile_band[1]))) if tile_band is not None else None
-        args = (P, int(degree), M, int(R), _ptr(background), W, H, ctypes.byref(st), band, _ptr(means3D), _ptr(sh),
+        # R (num_rendered) is part of the reference's signature; the library re-derives the arena carve-up from the
+        # size of the binning buffer instead, so a lazily resolved R never forces a host synchronisation here
+        args = (P, int(degree), M, int(binningBuffer.numel()), _ptr(background), W, H, ctypes.byref(st), band,
+                _ptr(means3D), _ptr(sh),
                 _ptr(opacities), _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
                 _ptr(viewmatrix), _ptr(projmatrix), _ptr(inv_viewprojmatrix), _ptr(campos), float(tan_fovx),
                 float(tan_fovy), _ptr(pixel_colors), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer),
@@ -391,11 +396,24 @@ def view_geometry(geomBuffer, P, settings_dict):
                 tiles_touched=_wrap(v.tiles_touched, geomBuffer, P, u32))
 
 
-def view_binning(binningBuffer, R):
+def view_binning(binningBuffer, R, settings_dict=None):
+    """point_list / point_list_keys (first R entries) of a binning arena.  The arena is carved for the capacity the
+    forward pass allocated, which follows from its size and -- because the depth-resorting modes add the per-tile
+    slabs -- from the settings; without settings both layouts are tried (only one reproduces the size exactly)."""
+    cap = None
+    cands = [settings_dict] if settings_dict is not None else [dict(sort_settings=dict(sort_mode=m)) for m in (0, 3)]
+    for d in cands:
+        st = StpSettings(int(d["sort_settings"]["sort_mode"]), *([0] * 12))
+        c = _lib.stp_binning_capacity(binningBuffer.numel(), ctypes.byref(st))
+        if _lib.stp_binning_bytes(c, ctypes.byref(st)) == binningBuffer.numel():
+            cap = c
+            break
+    if cap is None:
+        raise RuntimeError("binning buffer size does not match any arena layout")
     v = StpBinningView()
-    _lib.stp_view_binning(binningBuffer.data_ptr(), R, ctypes.byref(v))
-    return dict(point_list=_wrap(v.point_list, binningBuffer, R, torch.int32),
-                point_list_keys=_wrap(v.point_list_keys, binningBuffer, R, torch.int64))
+    _lib.stp_view_binning(binningBuffer.data_ptr(), cap, ctypes.byref(v))
+    return dict(point_list=_wrap(v.point_list, binningBuffer, cap, torch.int32)[:R],
+                point_list_keys=_wrap(v.point_list_keys, binningBuffer, cap, torch.int64)[:R])
 
 
 def view_image(imgBuffer, W, H):

@@ -51,6 +51,12 @@ def rasterize_gaussians(
     tile_band=None,
     sync_group=None,
 ):
+    # The blend log (2 KB per pixel) only pays off when a backward pass will follow.  Decided HERE, not inside
+    # Function.forward: there grad mode is always off and ctx.needs_input_grad reflects requires_grad even under
+    # torch.no_grad(), so evaluation renders of a trained model would record (and allocate) the log for nothing.
+    record_blends = torch.is_grad_enabled() and any(
+        isinstance(t, torch.Tensor) and t.requires_grad
+        for t in (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
     return _RasterizeGaussians.apply(
         means3D,
         means2D,
@@ -63,6 +69,7 @@ def rasterize_gaussians(
         raster_settings,
         tile_band,
         sync_group,
+        record_blends,
     )
 
 
@@ -71,10 +78,12 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, tile_band=None, sync_group=None):
+                raster_settings, tile_band=None, sync_group=None, record_blends=None):
         # tile_band (ours only, multi-GPU tile sharding): (row0, row1) of 16-pixel tile rows this rank renders
         # sync_group (ours only): process group over which backward sums the parameter gradients (overlapped exchange)
         rs = raster_settings
+        if record_blends is None:  # direct .apply callers: the wrapper above knows better (grad mode)
+            record_blends = any(ctx.needs_input_grad)
         args = (
             rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
             rs.viewmatrix, rs.projmatrix, rs.inv_viewprojmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
@@ -86,14 +95,14 @@ class _RasterizeGaussians(torch.autograd.Function):
             cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
             try:
                 num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(
-                    *args, record_blends=any(ctx.needs_input_grad), tile_band=tile_band)
+                    *args, record_blends=record_blends, tile_band=tile_band)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
             num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(
-                *args, record_blends=any(ctx.needs_input_grad), tile_band=tile_band)
+                *args, record_blends=record_blends, tile_band=tile_band)
 
         ctx.raster_settings = rs
         ctx.tile_band = tile_band
@@ -135,6 +144,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_scales,
             grad_rotations,
             grad_cov3Ds_precomp,
+            None,
             None,
             None,
             None,

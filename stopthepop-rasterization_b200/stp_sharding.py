@@ -50,8 +50,9 @@ def row_weights_from_ranges(ranges: torch.Tensor, grid_x: int, grid_y: int) -> t
 
 
 def all_reduce_param_grads(slab: torch.Tensor, group=None) -> torch.Tensor:
-    """the one gradient exchange of both sharding schemes: in-place all-reduce(sum) of the flat slab
-    [means3D(3P) | sh(3MP) | opacity(P) | scales(3P) | rot(4P)]."""
+    """the one gradient exchange of view sharding: in-place all-reduce(sum) of the flat parameter-gradient slab of
+    _C.rasterize_gaussians_backward(want_param_slab=True).  Slab order: [sh(3MP) | means3D(3P) | scales(3P) | rot(4P) |
+    opacity(P)], every sub-array starting on a multiple of 4 floats -- slice it with split_param_slab, never by hand."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(slab, op=dist.ReduceOp.SUM, group=group)
     return slab

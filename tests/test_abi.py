@@ -49,7 +49,9 @@ def test_abi_version_and_arena_sizes(lib):
     lib.stp_image_bytes.restype = ctypes.c_size_t
     lib.stp_image_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.stp_binning_bytes.restype = ctypes.c_size_t
-    lib.stp_binning_bytes.argtypes = [ctypes.c_int]
+    lib.stp_binning_bytes.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib.stp_binning_capacity.restype = ctypes.c_int
+    lib.stp_binning_capacity.argtypes = [ctypes.c_size_t, ctypes.c_void_p]
     P = 1000
     # 87 B per Gaussian of the reference layout minus the 4 B internal_radii and the 4 B point_offsets
     # we do not keep (slots are claimed per tile, binning.cu), +48 B with the inverse covariance
@@ -58,8 +60,22 @@ def test_abi_version_and_arena_sizes(lib):
     assert lib.stp_image_bytes(1920, 1080, 0) >= 8 * 1920 * 1080 + 8 * 120 * 68
     # HIER blend log: 8 B per (pixel of a whole tile, record)
     assert lib.stp_image_bytes(1920, 1080, 16) - lib.stp_image_bytes(1920, 1080, 0) >= 120 * 68 * 256 * 16 * 8
-    assert lib.stp_binning_bytes(10) >= 28 * 10  # point_list + sorted keys + bucket + merge scratch
-    assert lib.stp_binning_bytes(0) > 0
+    assert lib.stp_binning_bytes(10, None) >= 28 * 10  # point_list + sorted keys + bucket + merge scratch
+    assert lib.stp_binning_bytes(0, None) > 0
+    # the depth-resorting modes add one 64-byte slab record per instance; capacity <-> size is an exact bijection on
+    # multiples of 64 instances (the backward pass re-derives the carve-up from the arena size alone)
+    from diff_gaussian_rasterization import _C
+    hier = _C.StpSettings(3, *([0] * 12))
+    glob = _C.StpSettings(0, *([0] * 12))
+    for st in (hier, glob):
+        ref = ctypes.addressof(st)
+        for cap in (0, 1, 63, 64, 65, 1000, 6381641):
+            nbytes = lib.stp_binning_bytes(cap, ref)
+            rounded = (cap + 63) // 64 * 64
+            assert lib.stp_binning_capacity(nbytes, ref) == rounded
+            assert lib.stp_binning_bytes(rounded, ref) == nbytes
+    assert (lib.stp_binning_bytes(6400, ctypes.addressof(hier)) - lib.stp_binning_bytes(6400, ctypes.addressof(glob))
+            == 64 * 6400)
 
 
 def test_settings_validation_without_gpu(lib):
