@@ -1,13 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: sorted-Gaussian rasterizer forward + backward (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3a|C3b|C1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3b|C2|C3a|C4|C5|C1]
+                    [--sharding auto|bands|views] [--no-extras]
 
 A "step" is one fwd+bwd pass of the rasterizer over one view of the synthetic cloud of SURVEY 8(d).
-N=1 workload = BASELINE.json configs[1]: 1M Gaussians, 1920x1080, GLOBAL sort mode, fwd+bwd.
-N>1: view sharding (SURVEY 8e / north_star "or batched views"): every rank holds the same Gaussians and
-renders its own camera (yaw = rank * 0.08 rad), then ONE NCCL all-reduce(sum) of the flat parameter-gradient
-slab -- the data-parallel training step; per-GPU work is fixed => "scaling": "weak".
+Default workload = the configuration north_star's target is quoted on (BASELINE.json configs[2], "C3b"):
+4M Gaussians, 1920x1080, StopThePop preset (HIER sort, per-tile depth, tile / 4x4 culling), fwd+bwd.
+N>1 (default sharding of C3a / C3b / C4): ONE frame, tile-row bands sharded across the ranks (north_star: "sharding
+screen-space tile ranges ... >= 6x aggregate at 8 GPUs tile-sharded"): every rank holds the same Gaussians,
+preprocesses all of them, bins / sorts / renders only its band (bands balanced by the instance counts of a warm-up
+frame); exchange = ONE NCCL all-gather of the image bands (forward) and ONE all-reduce of the 48 B/Gaussian packed
+screen-space gradient accumulator (backward), after which every rank finishes the per-Gaussian backward and holds the
+full gradients.  Total work is fixed => "scaling": "strong".
+--sharding views (default of C2 / C5): one camera per rank (yaw = rank * 0.08 rad), ONE logical all-reduce of the
+parameter-gradient slab, overlapped with the preprocess-backward stage; per-GPU work fixed => "weak".
 
 Printed JSON line (rank 0):
   value     Mpixels/s, whole job, Gaussians + camera + upstream gradient resident in HBM (CUDA events, max over ranks)
@@ -16,11 +23,16 @@ Printed JSON line (rank 0):
             to the host inside the timed region.  The Gaussian parameters are the model state and stay resident.
             `e2e_full_upload` additionally uploads every Gaussian parameter and downloads every gradient.
   roofline  dominant kernel: algorithmic bytes (SURVEY 8d formula at the measured P,V,R) / CUDA-event time of
-            that kernel averaged over the timed steps (stage events recorded inside the library, resolved lazily)
+            that kernel averaged over the timed steps (stage events recorded inside the library, resolved lazily);
+            `traffic` = DRAM bytes of that kernel from the committed ncu capture named in `traffic_source`
+  extra     short measurements of the other BASELINE.json configurations in the same run (N=1: C2, C4; N>1: C4 tile
+            bands), each with its own value / e2e / stage times -- not the headline
   cpu_baseline  the plain-C oracle port (OpenMP, all host cores) on a bounded sample, N=1 only
 --impl reference: the reference's own implementation.  The reference ships NO CPU path, so this
 arm times the UNMODIFIED reference CUDA build (oracle/_ref, compiled from /root/reference for sm_100) on the same
 GPU through its own _C API, same workload, same copies; if oracle/_ref is absent it falls back to the C oracle port.
+The reference cannot shard a frame: for tile-band workloads at N>1 rank 0 alone runs the whole frame on one GPU
+("for C4 at 2/4/8 GPUs the baseline stays the 1-GPU reference number") and the other ranks exit.
 """
 import argparse
 import json
@@ -51,7 +63,8 @@ WORKLOADS = {
     # BASELINE.json configs[4]: 10M Gaussians, one 1080p view per rank (8 views at 8 GPUs), StopThePop preset
     "C5": ("C5", dict(S.STOPTHEPOP_PRESET), "C5: 10M Gaussians, one 1920x1080 view per rank, StopThePop preset, fwd+bwd"),
 }
-BAND_SHARDED = {"C4"}  # strong scaling: all ranks render ONE frame; everything else: one view per rank (weak scaling)
+# default multi-GPU split: tile-row bands of ONE frame (strong scaling) / one view per rank (weak scaling)
+BAND_DEFAULT = {"C3a", "C3b", "C4"}
 
 
 class ClockSampler:
@@ -237,93 +250,70 @@ def cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, repeats):
     return (time.perf_counter() - t0) / repeats
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--points", type=int, default=0, help="override the number of Gaussians of the workload's scene")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--trace-steps", action="store_true", help="diagnostics: per-step times of every timed region")
-    a = ap.parse_args()
-    a.warmup = max(a.warmup, 3)
+def own_sort_bytes(R, T, slab):
+    """what the tile-bucket sort of this library moves per launch: 8 B record in, 12 B (key + id) out and, for the
+    depth-resorting modes, the slab record (72 B gathered, 64 B written) -- next to SURVEY 8d's radix-sort formula"""
+    return R * (8 + 12 + (136 if slab else 0)) + 16 * T
 
-    global TRACE_STEPS
-    TRACE_STEPS = a.trace_steps
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    scene_name, overrides, desc = WORKLOADS[a.workload]
+
+def bands_mode_of(workload, sharding, world):
+    if world <= 1:
+        return False
+    if sharding == "auto":
+        return workload in BAND_DEFAULT
+    return sharding == "bands"
+
+
+def measure(a, workload, world, rank, dev, steps, warmup, full):
+    """one workload on the current process group -> dict (rank 0) / None.  full: e2e_full_upload, roofline details,
+    cpu_baseline; extras run with full=False."""
+    scene_name, overrides, desc = WORKLOADS[workload]
     settings = S.default_settings_dict(**overrides)
     cid, P, W, H = S.CONFIGS[scene_name]
-    if a.points:
+    if a.points and full:
         P = a.points
         desc += f" [--points {P}]"
     pixels = W * H
-    bands_mode = a.workload in BAND_SHARDED
+    bands_mode = bands_mode_of(workload, a.sharding, world)
+    ref_single = a.impl == "reference" and bands_mode  # the reference cannot shard a frame: one GPU renders all of it
+    eff_world = 1 if ref_single else world
+    use_dist = eff_world > 1
 
-    ref, use_ref_gpu = None, False
-    if a.impl == "reference":  # the only arm that touches oracle/ (besides the cpu_baseline leg below)
+    ref = None
+    if a.impl == "reference":
         from oracle import ref_api as ref
-        use_ref_gpu = ref.available() and torch.cuda.is_available()
 
-    if a.impl == "reference" and not use_ref_gpu:
-        # no reference CUDA build travelled with the repo: the C oracle port on the host cores
-        if rank != 0:
-            return
-        sc_c, cam_c = S.make_config(scene_name, P=P)
-        dL_c = S.make_upstream_grad(W, H, 2000 + cid)
-        for _ in range(1):
-            cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, 1)
-        sec = cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, max(1, min(a.steps, 3)))
-        v = pixels / sec / 1e6
-        print(json.dumps({"impl": "reference", "metric": "Mpixels/s fwd+bwd", "value": v, "unit": "Mpixels/s",
-                          "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": {"workload": desc},
-                          "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "port",
-                                           "sample": "full workload, oracle/stp_oracle.c with OpenMP"},
-                          "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
-
-    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
-
-    # ---- workload: same Gaussians on every rank, one camera per rank ---------------------------------------
+    # ---- workload: same Gaussians on every rank; one camera per rank (views) or one camera for all (bands) ----
     sc_c, cam0_c = S.make_config(scene_name, P=P)
-    cam_c, _, _ = S.make_camera(W, H, yaw=0.0 if bands_mode else 0.08 * rank)
-    dL_c = S.make_upstream_grad(W, H, 2000 + cid + (0 if bands_mode else rank))
+    per_rank_view = use_dist and not bands_mode
+    cam_c, _, _ = S.make_camera(W, H, yaw=0.08 * rank if per_rank_view else 0.0)
+    dL_c = S.make_upstream_grad(W, H, 2000 + cid + (rank if per_rank_view else 0))
     import stp_sharding as SH
     grid_y = (H + 15) // 16
-    bands = SH.equal_bands(grid_y, world) if bands_mode else None
-    my_band = bands[rank] if bands_mode and world > 1 else None
+    grid_x = (W + 15) // 16
+    bands = SH.equal_bands(grid_y, world) if bands_mode and not ref_single else None
     sc, cam = S.to_device(sc_c, dev), S.to_device(cam_c, dev)
     dL = dL_c.to(dev)
     e = torch.empty(0, device=dev)
     M = sc.shs.shape[1]
+    band_box = {"band": bands[rank] if bands else None}
 
-    # ours: the gradient all-reduce is issued by the library, overlapped with the preprocess-backward stage (_C.py)
-    sync_group = dist.group.WORLD if (world > 1 and a.impl == "ours") else None
+    sync_group = dist.group.WORLD if (use_dist and a.impl == "ours") else None
     if a.impl == "ours":
         from diff_gaussian_rasterization import (ExtendedSettings, GaussianRasterizationSettings, GaussianRasterizer, _C)
 
         def fwd(c, dbg=2):
             return _C.rasterize_gaussians(c.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e,
                                           c.viewmatrix, c.projmatrix, c.inv_viewprojmatrix, c.tanfovx, c.tanfovy, H, W,
-                                          sc.shs, sc.sh_degree, c.campos, False, settings, False, dbg, tile_band=my_band)
+                                          sc.shs, sc.sh_degree, c.campos, False, settings, False, dbg,
+                                          tile_band=band_box["band"])
 
         def bwd(c, out, g, dbg=2):
             return _C.rasterize_gaussians_backward(c.bg, sc.means3D, out[2], sc.opacities, e, sc.scales, sc.rotations,
                                                    1.0, e, c.viewmatrix, c.projmatrix, c.inv_viewprojmatrix, c.tanfovx,
                                                    c.tanfovy, out[1], g, sc.shs, sc.sh_degree, c.campos, out[3], out[0],
                                                    out[4], out[5], settings, dbg, want_param_slab=True,
-                                                   tile_band=my_band, sync_group=sync_group)
+                                                   tile_band=band_box["band"], sync_group=sync_group)
     else:
         def fwd(c, dbg=False):
             return ref.forward(sc, c, settings)
@@ -333,18 +323,28 @@ def main():
             return grads, grads  # the reference returns 8 separate tensors
 
     state = {}
-
     full_sort_ref = a.impl == "reference" and settings["sort_settings"]["sort_mode"] == 1  # the reference has no backward
+
+    if bands is not None and a.bands == "balanced":
+        # bands of (almost) equal instance count instead of equal height: per-row instance counts of one warm-up frame
+        # rendered with equal bands, summed over the ranks ("balanced by instance count ... from the
+        # previous frame")
+        out0 = fwd(cam, dbg=0)
+        rows = SH.row_weights_from_ranges(_C.view_image(out0[5], W, H)["ranges"], grid_x, grid_y).to(torch.float32)
+        dist.all_reduce(rows)
+        bands = SH.balanced_bands(rows.cpu().tolist(), world)
+        band_box["band"] = bands[rank]
+        del out0
 
     def step_resident():
         out = fwd(cam)
-        if bands_mode and world > 1 and a.impl == "ours":
+        if bands is not None:
             state["image"] = SH.gather_image_bands(out[1], bands)  # the ONE forward exchange of tile sharding
         if full_sort_ref:
             state["out"] = out
             return
         grads, slab = bwd(cam, out, dL)
-        if world > 1 and a.impl != "ours":
+        if use_dist and a.impl != "ours":
             for t in (slab[3], slab[5], slab[2], slab[6], slab[7]):
                 dist.all_reduce(t)
         state["out"], state["grads"] = out, grads
@@ -364,6 +364,7 @@ def main():
     copy_stream = torch.cuda.Stream(device=dev)
     g_dev = torch.empty_like(dL)
     ev_g, ev_f = torch.cuda.Event(), torch.cuda.Event()
+    ext_settings = ExtendedSettings.from_dict(settings) if a.impl == "ours" else None
 
     def step_e2e():
         main = torch.cuda.current_stream(dev)
@@ -375,18 +376,19 @@ def main():
         for t in leaves + [means2D]:
             t.grad = None
         m3, op, sh, scl, rot = leaves
+        color_full = None
         if a.impl == "ours":
             rs = GaussianRasterizationSettings(H, W, cam_c.tanfovx, cam_c.tanfovy, bg, 1.0, vm, pm, iv, sc.sh_degree, cp,
                                                False, ext_settings, False, False)
-            color, radii = GaussianRasterizer(rs, tile_band=my_band, sync_group=sync_group)(
+            color, radii = GaussianRasterizer(rs, tile_band=band_box["band"], sync_group=sync_group)(
                 m3, means2D, op, shs=sh, scales=scl, rotations=rot)
-            if bands_mode and world > 1:
+            if bands is not None:
                 color_full = SH.gather_image_bands(color.detach(), bands)
         else:
             c = cam._replace(viewmatrix=vm, projmatrix=pm, inv_viewprojmatrix=iv, campos=cp, bg=bg)
             out = ref.forward(sc, c, settings)
             color = out[1]
-        img_out = color_full if (a.impl == "ours" and bands_mode and world > 1) else color.detach()
+        img_out = color_full if color_full is not None else color.detach()
         ev_f.record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_f)
@@ -397,19 +399,16 @@ def main():
             main.wait_stream(copy_stream)
             return
         if a.impl == "ours":
-            color.backward(g_dev)  # parameter gradients come back already summed over the ranks (sync_group)
+            color.backward(g_dev)  # gradients come back already summed over the ranks (sync_group)
         else:
             grads = ref.backward(sc, c, settings, out, g_dev)
-            if world > 1:
+            if use_dist:
                 for t in (grads[3], grads[5], grads[2], grads[6], grads[7]):
                     dist.all_reduce(t)
         main.wait_stream(copy_stream)
 
-    if a.impl == "ours":
-        ext_settings = ExtendedSettings.from_dict(settings)
-
     # full-upload variant: every Gaussian parameter host->device, every parameter gradient device->host
-    h_params = [pin(t) for t in (sc_c.means3D, sc_c.opacities, sc_c.shs, sc_c.scales, sc_c.rotations)]
+    h_params = [pin(t) for t in (sc_c.means3D, sc_c.opacities, sc_c.shs, sc_c.scales, sc_c.rotations)] if full else []
     h_grads = [torch.empty_like(t).pin_memory() for t in h_params]
     h2d_full = h2d + sum(t.numel() * 4 for t in h_params)
     d2h_full = d2h + sum(t.numel() * 4 for t in h_grads)
@@ -423,53 +422,58 @@ def main():
                 hg.copy_(t.grad, non_blocking=True)
 
     # ---- timed regions --------------------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # before the warm-up: nvidia-smi's start-up cost stays outside the timed region
+    tw = eff_world
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0 and full:
+        sampler.start()  # before the warm-up: the sampler's start-up cost stays outside the timed region
+    launches0 = 0
     if a.impl == "ours":
         _C.timing_reset()
-        warm_up(step_resident, a.warmup, world, MIN_WARM_S)
+        warm_up(step_resident, warmup, tw, MIN_WARM_S)
         _C.timing_reset()
         launches0 = _C.kernel_launches()
-    if rank == 0:
+    if rank == 0 and full:
         sampler.mark()  # only samples taken from here on (= during the timed region) are reported
-    ms_total = event_time_ms(step_resident, a.steps, a.warmup if a.impl != "ours" else 0, world,
+    ms_total = event_time_ms(step_resident, steps, warmup if a.impl != "ours" else 0, tw,
                              MIN_WARM_S if a.impl != "ours" else 0.0)
+    launches, stages = 0, {}
     if a.impl == "ours":
         launches = _C.kernel_launches() - launches0
         stages = _C.timing_summary()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = ms_total / a.steps
-    views = 1 if bands_mode else world  # tile sharding: all ranks render ONE frame (strong scaling)
+    clocks = sampler.stop() if (rank == 0 and full) else None
+    ms_step = ms_total / steps
+    views = eff_world if per_rank_view else 1  # tile sharding: all ranks render ONE frame (strong scaling)
     value = views * pixels / (ms_step * 1e-3) / 1e6
 
-    ms_e2e = event_time_ms(step_e2e, a.steps, a.warmup, world) / a.steps
+    ms_e2e = event_time_ms(step_e2e, steps, warmup, tw) / steps
     e2e_value = views * pixels / (ms_e2e * 1e-3) / 1e6
     e2e_full = None
-    if a.impl == "ours" and world == 1:
-        ms_full = event_time_ms(step_e2e_full, max(3, a.steps // 4), 3, world) / max(3, a.steps // 4)
+    if a.impl == "ours" and world == 1 and full:
+        ms_full = event_time_ms(step_e2e_full, max(3, steps // 4), 3, tw) / max(3, steps // 4)
         e2e_full = {"value": pixels / (ms_full * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d_full,
                     "d2h_bytes_per_step": d2h_full}
-
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     out = state["out"]
     R = int(out[0])
     V = int((out[2] > 0).sum().item())
-    line = {
-        "metric": "Mpixels/s fwd+bwd", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong" if bands_mode else "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "P": P, "W": W, "H": H, "visible": V, "num_rendered": R,
-                   "sharding": ("tile-row bands of one view (replicated Gaussians, NCCL all-gather of the image bands + "
-                                "all-reduce of parameter grads)" if bands_mode else
-                                "views (one camera per rank, replicated Gaussians, NCCL all-reduce of parameter grads, "
-                                "overlapped with the preprocess-backward stage)")
-                   if world > 1 else "single GPU",
+    if bands is None and world == 1:
+        sharding = "single GPU"
+    elif ref_single:
+        sharding = ("reference arm: ONE GPU renders the whole frame (the reference cannot shard a frame; SURVEY 8d keeps "
+                    "the 1-GPU reference number as the baseline of the tile-sharded configurations)")
+    elif bands is not None:
+        sharding = (f"tile-row bands of one view ({a.bands}: {bands}); replicated Gaussians, NCCL all-gather of the image "
+                    "bands + all-reduce of the 48 B/Gaussian screen-space gradient accumulator between the two backward "
+                    "stages")
+    else:
+        sharding = ("views (one camera per rank, replicated Gaussians, NCCL all-reduce of parameter grads, overlapped "
+                    "with the preprocess-backward stage)")
+    res = {
+        "value": value, "ms_per_step": ms_step, "steps": steps,
+        "scaling": "strong" if (bands_mode or (world == 1 and workload in BAND_DEFAULT and a.sharding != "views")) else "weak",
+        "config": {"workload": desc, "P": P, "W": W, "H": H, "visible": V, "num_rendered": R, "sharding": sharding,
                    "l2_policy": "inputs larger than L2 (236 B/Gaussian x P + instance lists >> 126 MB)" if P >= 10**6
                    else "small parity config; L2-resident"},
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -479,11 +483,13 @@ def main():
                         "streams are done); Gaussian parameters (model state) resident"},
         "clocks": clocks,
     }
+    if bands is not None:
+        res["config"]["num_rendered_is"] = "rank 0's band only"
     if full_sort_ref:
-        line["config"]["note"] = ("reference arm is FORWARD ONLY: the reference has no PPX_FULL backward "
-                                  "(backward.cu:733-736); ours is forward + backward")
+        res["config"]["note"] = ("reference arm is FORWARD ONLY: the reference has no PPX_FULL backward "
+                                 "(backward.cu:733-736); ours is forward + backward")
     if a.impl == "ours":
-        N, T = pixels, ((W + 15) // 16) * ((H + 15) // 16)
+        N, T = pixels, grid_x * grid_y
         s_flag = 0 if settings["sort_settings"]["sort_mode"] == 0 else 1
         c_flag = 1 if (s_flag or settings["sort_settings"]["sort_order"] in (2, 3)) else 0
         ab = algorithmic_bytes(P, V, R, N, T, M, s_flag, c_flag)
@@ -493,50 +499,164 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        per_stage = {k: {"ms": v[0], "GBps": ab[k] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None, "bytes": ab[k]}
-                     for k, v in stages.items() if k in ab}
-        own = per_stage
-        dom = max(own, key=lambda k: own[k]["ms"])
-        traffic = issue_pct = None
+        prof = {}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            traffic = prof.get(a.workload, {}).get(dom)
-            issue_pct = prof.get(a.workload + "_issue_active_pct", {}).get(dom)
         except Exception:
             pass
-        line["roofline"] = {"bound": "hbm", "kernel": KERNEL_OF_STAGE[dom], "stage": dom,
-                            "achieved": per_stage[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                            "frac": per_stage[dom]["GBps"] / peak, "traffic": traffic,
-                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                            "algorithmic_bytes": ab[dom], "kernel_ms": per_stage[dom]["ms"],
-                            # what actually bounds the dominant kernel (ncu smsp__issue_active of the committed capture,
-                            # profiles/*_ncu_full_summary_*.csv): the render kernels are instruction-issue bound, not HBM bound
-                            "issue_active_pct_ncu": issue_pct,
-                            "stages": per_stage,
-                            "whole_step": {"bytes": sum(ab.values()), "GBps": sum(ab.values()) / (ms_step * 1e-3) / 1e9,
-                                           "frac": sum(ab.values()) / (ms_step * 1e-3) / 1e9 / peak}}
-        line["gpu_launches"] = int(launches)
+        measured = prof.get(workload, {}) if world == 1 else {}
+        per_stage = {}
+        for k, v in stages.items():
+            if k not in ab:
+                continue
+            row = {"ms": v[0], "GBps": ab[k] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None, "bytes": ab[k]}
+            if k == "Sort":
+                # SURVEY 8d charges the reference's six radix passes; the tile-bucket sort moves far fewer bytes, so the
+                # formula alone would show a "fraction" above 1 on bytes that are never moved: both are printed
+                row["bytes_is"] = "SURVEY 8d formula (reference radix sort: 6 passes x 24 B/instance)"
+                row["own_bytes"] = own_sort_bytes(R, T, bool(s_flag))
+                row["own_GBps"] = row["own_bytes"] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None
+            if k in measured:
+                row["dram_bytes_ncu"] = measured[k]
+            per_stage[k] = row
+        dom = max(per_stage, key=lambda k: per_stage[k]["ms"])
+        res["stages_ms"] = {k: round(v["ms"], 4) for k, v in per_stage.items()}
+        res["gpu_launches"] = int(launches)
+        if full:
+            res["roofline"] = {
+                "bound": "hbm", "kernel": KERNEL_OF_STAGE[dom], "stage": dom,
+                "achieved": per_stage[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": per_stage[dom]["GBps"] / peak, "traffic": measured.get(dom),
+                "traffic_source": (prof.get("_source", "committed ncu capture under profiles/") if measured.get(dom)
+                                   else "none for this workload / GPU count"),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                "algorithmic_bytes": ab[dom], "kernel_ms": per_stage[dom]["ms"],
+                # what actually bounds the dominant kernel (ncu smsp__issue_active of the committed capture,
+                # profiles/*_ncu_full_summary_*.csv): the render kernels are instruction-issue bound, not HBM bound
+                "issue_active_pct_ncu": prof.get(workload + "_issue_active_pct", {}).get(dom),
+                "stages": per_stage,
+                "whole_step": {"bytes": sum(ab.values()), "GBps": sum(ab.values()) / (ms_step * 1e-3) / 1e9,
+                               "frac": sum(ab.values()) / (ms_step * 1e-3) / 1e9 / peak}}
         if e2e_full:
-            line["e2e_full_upload"] = e2e_full
-        if world == 1 and not a.no_cpu_baseline and settings["sort_settings"]["sort_mode"] != 1:
+            res["e2e_full_upload"] = e2e_full
+        if world == 1 and full and not a.no_cpu_baseline and settings["sort_settings"]["sort_mode"] != 1:
             reps = 2 if P <= 10**6 else 1
             sc_b, cam_b, dL_b, sample = sc_c, cam_c, dL_c, f"{reps} full step(s) of the workload"
             if P > 10**6:  # bound the CPU work: same camera, first 1M Gaussians of the cloud
                 sc_b = S.Scene(*[t[:10**6].contiguous() if isinstance(t, torch.Tensor) else t for t in sc_c])
                 sample = "1 step over the first 1M Gaussians of the cloud at full resolution"
             sec = cpu_port_step_seconds(sc_b, cam_b, settings, dL_b, reps)
-            line["cpu_baseline"] = {"value": pixels / sec / 1e6, "unit": "Mpixels/s", "cores": os.cpu_count(),
-                                    "kind": "port", "sample": sample + " (oracle/stp_oracle.c, OpenMP)",
-                                    "ms_per_step": sec * 1e3}
+            res["cpu_baseline"] = {"value": pixels / sec / 1e6, "unit": "Mpixels/s", "cores": os.cpu_count(),
+                                   "kind": "port", "sample": sample + " (oracle/stp_oracle.c, OpenMP)",
+                                   "ms_per_step": sec * 1e3}
     else:
+        res["cpu_baseline"] = {"value": e2e_value, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "reference",
+                               "sample": "unmodified reference CUDA build (oracle/_ref, sm_100) on the same GPU, full "
+                                         "workload -- the reference ships no CPU path; host cores only launch kernels"}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3b", choices=sorted(WORKLOADS))
+    ap.add_argument("--sharding", default="auto", choices=["auto", "bands", "views"],
+                    help="multi-GPU split: tile-row bands of one frame / one view per rank (auto: per workload)")
+    ap.add_argument("--bands", default="balanced", choices=["balanced", "equal"],
+                    help="tile-row bands of equal instance count (from a warm-up frame) or of equal height")
+    ap.add_argument("--points", type=int, default=0, help="override the number of Gaussians of the workload's scene")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations")
+    ap.add_argument("--trace-steps", action="store_true", help="diagnostics: per-step times of every timed region")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    global TRACE_STEPS
+    TRACE_STEPS = a.trace_steps
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    scene_name, overrides, desc = WORKLOADS[a.workload]
+    settings = S.default_settings_dict(**overrides)
+    cid, P, W, H = S.CONFIGS[scene_name]
+
+    use_ref_gpu = False
+    if a.impl == "reference":  # the only arm that touches oracle/ (besides the cpu_baseline leg)
+        from oracle import ref_api as ref
+        use_ref_gpu = ref.available() and torch.cuda.is_available()
+
+    if a.impl == "reference" and not use_ref_gpu:
+        # no reference CUDA build travelled with the repo: the C oracle port on the host cores
+        if rank != 0:
+            return
+        sc_c, cam_c = S.make_config(scene_name, P=a.points or P)
+        dL_c = S.make_upstream_grad(W, H, 2000 + cid)
+        for _ in range(1):
+            cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, 1)
+        sec = cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, max(1, min(a.steps, 3)))
+        v = W * H / sec / 1e6
+        print(json.dumps({"impl": "reference", "metric": "Mpixels/s fwd+bwd", "value": v, "unit": "Mpixels/s",
+                          "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": desc},
+                          "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "port",
+                                           "sample": "full workload, oracle/stp_oracle.c with OpenMP"},
+                          "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    main_bands = bands_mode_of(a.workload, a.sharding, world)
+    # extras: short runs of the other BASELINE.json configurations, reported under "extra" (never the headline)
+    extras = []
+    if not a.no_extras and not a.points:
+        extras = [w for w in (("C2", "C4") if world == 1 else ("C4",)) if w != a.workload]
+        if world > 1:
+            extras = [w for w in extras if bands_mode_of(w, a.sharding, world) == main_bands]
+    ref_rank0_only = a.impl == "reference" and main_bands
+    if ref_rank0_only and rank != 0:
+        return  # the reference renders the whole frame on one GPU; nothing to do for the other ranks
+    if world > 1 and not ref_rank0_only:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+
+    res = measure(a, a.workload, world, rank, dev, a.steps, a.warmup, True)
+    extra = {}
+    for w in extras:
+        torch.cuda.empty_cache()
+        ws = max(3, min(a.steps, 5 if w == "C4" else 20))
+        if a.impl == "reference" and w == "C4":
+            ws = 3  # the reference's full per-pixel sort takes seconds per frame
+        r = measure(a, w, world, rank, dev, ws, 3, False)
+        if r is not None:
+            r.pop("clocks", None)
+            extra[w] = r
+    if rank != 0:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "Mpixels/s fwd+bwd", "value": res["value"], "unit": "Mpixels/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": res["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": res["config"], "e2e": res["e2e"], "clocks": res["clocks"],
+    }
+    for k in ("roofline", "gpu_launches", "e2e_full_upload", "cpu_baseline"):
+        if k in res:
+            line[k] = res[k]
+    if a.impl != "ours":
         line["impl"] = "reference"
-        line["cpu_baseline"] = {"value": e2e_value, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "reference",
-                                "sample": "unmodified reference CUDA build (oracle/_ref, sm_100) on the same GPU, full "
-                                          "workload -- the reference ships no CPU path; host cores only launch kernels"}
+    if extra:
+        line["extra"] = extra
     if TRACE_STEPS:
         line["step_trace_ms"] = STEP_TRACE
     print(json.dumps(line))
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 

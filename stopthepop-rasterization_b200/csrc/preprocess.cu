@@ -206,7 +206,10 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
                 mean2D = project_mean2d(f.projmatrix, x, y, z, f.W, f.H);
                 rect_ext.x = fminf(a.rect_bounding ? fmul(extent, fsqrt(ca)) : radius, radius);
                 rect_ext.y = fminf(a.rect_bounding ? fmul(extent, fsqrt(cc)) : radius, radius);
-                rc = tile_rect(mean2D, rect_ext, f.grid_x, f.grid_y, f.row0, f.row1);
+                // visibility (radii, the geometry state) never depends on a tile band: every rank of a tile-sharded frame
+                // holds the state of every visible Gaussian, so that the backward pass can be finished anywhere once
+                // the screen-space gradients are summed (stp_sharding.py).  Only the binning below is clamped to the band.
+                rc = tile_rect(mean2D, rect_ext, f.grid_x, f.grid_y, 0, f.grid_y);
                 tiles = (uint32_t)((rc.x1 - rc.x0) * (rc.y1 - rc.y0));
                 if (tiles == 0) alive = false;
             }
@@ -215,14 +218,24 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
 
     {
         // per-tile instance histogram (sizes the tile buckets of binning.cu) and, with tile_based_culling, the
-        // exact tile count: the owner thread visits the first kSeqTiles tiles, the warp shares the rest
-        const int rect_tiles = alive ? (int)tiles : 0;
+        // exact tile count: the owner thread visits the first kSeqTiles tiles, the warp shares the rest.
+        // Tile band (multi-GPU): only tiles of rows [row0,row1) are binned.  Without culling the walk is clamped to the
+        // band; with culling the whole rectangle is walked, because "some tile contributes" decides visibility.
+        const int by0 = min(f.row1, max(f.row0, rc.y0)), by1 = min(f.row1, max(f.row0, rc.y1));
+        if constexpr (!TBC) {
+            rc.y0 = by0;
+            rc.y1 = by1;
+        }
+        const int rect_tiles = alive ? (rc.x1 - rc.x0) * (rc.y1 - rc.y0) : 0;
         const int rw = max(rc.x1 - rc.x0, 1);
-        int count = 0;
+        int count = 0, count_band = 0;
         for (int t = 0, tx = rc.x0, ty = rc.y0; t < min(rect_tiles, kSeqTiles); ++t) {
             if (!TBC || tile_contributes(co.x, co.y, co.z, mean2D, thr, tx, ty)) {
                 ++count;
-                atomicAdd(tile_count + ty * f.grid_x + tx, 1u);
+                if (!TBC || (ty >= by0 && ty < by1)) {
+                    ++count_band;
+                    atomicAdd(tile_count + ty * f.grid_x + tx, 1u);
+                }
             }
             if (++tx == rc.x1) {
                 tx = rc.x0;
@@ -244,23 +257,33 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
             }
             const int x0 = __shfl_sync(0xffffffffu, rc.x0, src), y0 = __shfl_sync(0xffffffffu, rc.y0, src);
             const int w = __shfl_sync(0xffffffffu, rw, src), n = __shfl_sync(0xffffffffu, rect_tiles, src);
-            int c = 0;
+            const int sy0 = __shfl_sync(0xffffffffu, by0, src), sy1 = __shfl_sync(0xffffffffu, by1, src);
+            int c = 0, cb = 0;
             for (int t = kSeqTiles + lane; t < n; t += 32) {
                 const int tx = x0 + t % w, ty = y0 + t / w;
                 if (!TBC || tile_contributes(A, B, C, m, th, tx, ty)) {
                     ++c;
-                    atomicAdd(tile_count + ty * f.grid_x + tx, 1u);
+                    if (!TBC || (ty >= sy0 && ty < sy1)) {
+                        ++cb;
+                        atomicAdd(tile_count + ty * f.grid_x + tx, 1u);
+                    }
                 }
             }
             if constexpr (TBC) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                if (lane == src) count += c;
+                for (int o = 16; o > 0; o >>= 1) {
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
+                    cb += __shfl_xor_sync(0xffffffffu, cb, o);
+                }
+                if (lane == src) {
+                    count += c;
+                    count_band += cb;
+                }
             }
         }
-        if (TBC && alive) {
-            tiles = (uint32_t)count;
-            if (tiles == 0) alive = false;
+        if (alive) {
+            if (TBC && count == 0) alive = false;  // no tile of the image sees it
+            tiles = TBC ? (uint32_t)count_band : (uint32_t)rect_tiles;  // instances this rank bins
         }
     }
     if (!alive) tiles = 0;

@@ -16,37 +16,49 @@
 //   * every pixel first blends its head minimum if the head is full, then evaluates the entry on its
 //     own ray (depth < 0, power > 0, alpha < 1/255 reject) and inserts it by strict '<';
 //   * drain order tail -> mid -> head.
-// How it is done is new: one warp owns two 4x4 blocks (one per half-warp), all queue manipulation is
-// rank based (every lane computes the final position of "its" entries with branch-free counting /
-// binary search and scatters them once) instead of compare-exchange networks with a barrier per
-// stage; queues are addressed through base offsets so popping never moves data; warps of one tile
-// run independently (no CTA barrier in the streaming loop), so a finished 8x4 region retires early.
+//
+// How it is done is new.
+//   Data movement.  The tile's Gaussians are not gathered through their ids: the tile-sort epilogue has
+//   written one 64-byte record per instance in list order (stp_slab.cuh).  The tail stage reads them from
+//   a shared-memory ring that is filled 32 records (2 KB) at a time with bulk-async copies (TMA,
+//   cp.async.bulk + mbarrier), shared by the eight warps of the tile; the queues carry tile-local list
+//   positions, and the mid / head stages read "their" record from the (L1/L2-resident) slab.
+//   Queues.  One warp owns two 4x4 blocks (one per half-warp); all queue manipulation is rank based
+//   (every lane computes the final position of "its" entries with branch-free counting / binary search
+//   and scatters them once) instead of compare-exchange networks with a barrier per stage; queues are
+//   addressed through base offsets so popping never moves data.
+//   Head stage.  A pixel's result depends only on the ORDER in which its quad hands it entries, not on
+//   when: the pop "if the head is full" that precedes every arrival only matters before an entry that
+//   is actually inserted.  So the mid stage does not call the pixels; it appends the popped positions
+//   to a per-quad ring, and the pixels consume that stream at their own pace: every lane scans forward
+//   (cheap alpha test) until it holds a survivor, and the expensive part -- depth on the pixel's ray,
+//   head insertion, blending of the popped minimum -- runs for the whole warp once most lanes hold one.
+//   With the lock-step version only the few pixels that pass the alpha test did useful work in that
+//   part, and the two half-warps of a warp (different blocks, different pop times) never overlapped.
 // The per-pixel arithmetic is the rounding-pinned sequence of stp_math.cuh.
 #include "stp_kernels.cuh"
+#include "stp_slab.cuh"
 
-#ifndef STP_HIER_SPEC
-#define STP_HIER_SPEC 0
+#ifndef STP_HIER_MINB_FWD  // resident CTAs per SM asked from ptxas: the kernels are latency / issue bound and
+#define STP_HIER_MINB_FWD 4  // occupancy limited by registers
 #endif
-#ifndef STP_HIER_MIDBATCH
-#define STP_HIER_MIDBATCH 0
-#endif
-#ifndef STP_HIER_MINB_FWD  // resident CTAs per SM asked from ptxas (register cap 48 / 64): the kernels are latency bound and
-#define STP_HIER_MINB_FWD 5  // occupancy limited by registers; A/B on B200: fwd 3->5 CTAs -22 %, bwd 3->4 CTAs -10 % (5: worse, spills)
-#endif
-#ifndef STP_HIER_MINB_FWD_CULL  // the 4x4-culling forward variant keeps more state live: 4 CTAs (64 registers) beat 5 there
+#ifndef STP_HIER_MINB_FWD_CULL
 #define STP_HIER_MINB_FWD_CULL 4
 #endif
 #ifndef STP_HIER_MINB_BWD
-#define STP_HIER_MINB_BWD 4
+#define STP_HIER_MINB_BWD 3
 #endif
-#ifndef STP_HIER_FIFO      // defer mid/head work through the per-block FIFO until both blocks of a warp have a group
-#define STP_HIER_FIFO 0
+#ifndef STP_HIER_THRESH    // lanes that must hold a survivor before the warp runs the insertion / blending step
+#define STP_HIER_THRESH 20
+#endif
+#ifndef STP_HIER_SCAN      // ring entries a lane may scan between two warp votes
+#define STP_HIER_SCAN 2
+#endif
+#ifndef STP_HIER_RING      // per-quad stream ring (entries, power of two >= 64: one batch can append 32)
+#define STP_HIER_RING 64
 #endif
 #ifndef STP_HIER_COMPACT   // with 4x4 culling: compact the surviving entries of a batch before ranking them
 #define STP_HIER_COMPACT 1
-#endif
-#ifndef STP_HIER_PREFILTER // with 4x4 culling: bounding-box rejection before the exact contribution test
-#define STP_HIER_PREFILTER 0
 #endif
 
 namespace stp {
@@ -54,25 +66,30 @@ namespace stp {
 namespace {
 
 constexpr float kFltMax = 3.402823466e+38f;
-constexpr int kDeadBit = 0x40000000;  // entry cannot reach any pixel of the 4x4 block (ids are < 2^30)
-constexpr int kIdMask = 0x3fffffff;
+constexpr int kDeadBit = 0x40000000;  // entry cannot reach any pixel of the 4x4 block (list positions are < 2^30)
+constexpr int kIdxMask = 0x3fffffff;
+constexpr float kPowerReject = -5.6f;  // ln(1/255) = -5.541: below this, opacity * exp(power) < 1/255 for any opacity <= 1
 constexpr int kTailStride = 80;  // 64 entries + 16 pad: the two blocks of a warp live in disjoint banks
-constexpr int kFifoGroups = 16;  // capacity of the tail -> mid hand-over queue of a block, in groups of 4 ids
-constexpr int kFifoIds = kFifoGroups * 4;
-constexpr int kFifoLimit = 8;    // backlog a block may keep while the other block of its warp has nothing to do
+constexpr int kStages = 4;       // slab ring: batches of 32 records in flight / being read
+constexpr int kBatch = 32;
+constexpr int kRing = STP_HIER_RING;  // per-quad stream ring (entries); one batch can append at most 32
+constexpr int kWarps = 8;
 
 template <int MID>
 struct HierShared {
     static constexpr int kMidCap = MID - 4;       // resident entries after a pop
     static constexpr int kMidStride = MID - 3;    // odd stride: the 8 quads of a warp hit distinct banks
+    float4 slab[kStages][kBatch * kSlabChunks];   // TMA destination, 2 KB per stage
+    uint64_t full[kStages];                       // mbarrier per stage: the batch has landed
+    uint32_t released[kStages];                   // warps that are done with the stage's current batch
     float tail_d[16 * kTailStride];
     int tail_id[16 * kTailStride];
     float new_d[16 * 48];  // 32 entries per block, stride 48 (16-bank offset between the blocks of a warp)
     int new_id[16 * 48];
     float mid_d[64 * kMidStride];
     int mid_id[64 * kMidStride];
-    int out_id[64 * 4];
-    int fifo_id[16 * kFifoIds];  // popped tail groups waiting for the mid stage, per block
+    int ring[64 * kRing];  // per quad: list positions popped by the mid queue, in order
+    int popped[64 * 4];    // per quad: the group that is leaving the mid queue
     float tail_ray[16 * 3];
     float mid_ray[64 * 3];
     float pix_ray[3 * 256];  // per-pixel view ray, [component][thread]: only read by the few entries that pass the alpha test
@@ -83,20 +100,6 @@ struct HierShared {
 struct HierSharedBwd {
     float pix_const[8 * 256];
 };
-
-struct GaussRec {
-    float2 xy;
-    float4 co;
-    float ic[6];
-    float ux, uy, uz;
-};
-
-__device__ __forceinline__ void load_inv(const float4* __restrict__ inv, int id, float* ic, float& ux, float& uy, float& uz) {
-    const float4 a = __ldg(inv + 3 * id), b = __ldg(inv + 3 * id + 1), c = __ldg(inv + 3 * id + 2);
-    ic[0] = a.x; ic[1] = a.y; ic[2] = a.z;
-    ic[3] = b.x; ic[4] = b.y; ic[5] = b.z;
-    ux = c.x; uy = c.y; uz = c.z;
-}
 
 // true if no pixel of the 4x4 block at (bx0,by0) can see alpha >= 1/255 from this Gaussian: real q(d) <= thr implies
 // |dx| <= sqrt(2 thr C/det), |dy| <= sqrt(2 thr A/det); thr inflated by 0.1 % + 0.01, half-widths by 0.01 px.
@@ -111,22 +114,10 @@ __device__ __forceinline__ bool block_unreachable(float2 xy, float4 co, float bx
     return (xy.x + hx < bx0) || (xy.x - hx > bx0 + 3.0f) || (xy.y + hy < by0) || (xy.y - hy > by0 + 3.0f);
 }
 
-// per-pixel blending state
-template <bool BWD>
-struct PixelState;
-template <>
-struct PixelState<false> {
-    float T, C0, C1, C2;
-};
-template <>
-struct PixelState<true> {
-    float T, C0, C1, C2;
-};
-
 template <int HEAD, int MID, bool CULL, bool BWD>
 __global__ void __launch_bounds__(256, (HEAD <= 4 && MID <= 12) ? (BWD ? STP_HIER_MINB_BWD : (CULL ? STP_HIER_MINB_FWD_CULL : STP_HIER_MINB_FWD)) : 1)
 render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     using Sh = HierShared<MID>;
     Sh& sh = *reinterpret_cast<Sh*>(smem_raw);
     float* const pc = reinterpret_cast<HierSharedBwd*>(smem_raw + sizeof(Sh))->pix_const + threadIdx.x;  // BWD only
@@ -153,11 +144,32 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     }
 
     const uint2* __restrict__ ranges = BWD ? ab.ranges : a.ranges;
-    const uint32_t* __restrict__ point_list = BWD ? ab.point_list : a.point_list;
+    const float4* __restrict__ slab = BWD ? ab.slab : a.slab;
     const float2* __restrict__ means2D = BWD ? ab.means2D : a.means2D;
     const float4* __restrict__ conic_opacity = BWD ? ab.conic_opacity : a.conic_opacity;
-    const float4* __restrict__ cov3D_inv = BWD ? ab.cov3D_inv : a.cov3D_inv;
     const float* __restrict__ colors = BWD ? ab.colors : a.colors;
+
+    const uint2 range = ranges[tile_lin];
+    const uint32_t first = range.x;                      // absolute list position of the tile's first instance
+    const int n = (int)(range.y - range.x);
+    const int nb = (n + kBatch - 1) / kBatch;            // batches of 32 list entries
+
+    // ---- slab ring: the first kStages batches are requested before anything else happens ------------------------------
+    auto request_batch = [&](int k) {  // one thread
+        const int s = k % kStages;
+        const uint32_t bytes = (uint32_t)min(kBatch, n - k * kBatch) * kSlabRecordBytes;
+        mbar_expect_tx(&sh.full[s], bytes);
+        bulk_g2s(sh.slab[s], slab + (size_t)kSlabChunks * (first + (uint32_t)k * kBatch), bytes, &sh.full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&sh.full[s], 1);
+            sh.released[s] = 0u;
+        }
+        mbar_fence_init();
+        for (int k = 0; k < min(nb, kStages); ++k) request_batch(k);
+    }
 
     const RayCam cam = make_raycam(f.inv_viewproj, f.cam_pos, f.W, f.H);
     {
@@ -172,11 +184,8 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         const Vec3 r = view_ray(cam, fadd((float)cx, 0.5f + 2.0f * (q & 1)), fadd((float)cy, 0.5f + 2.0f * (q >> 1)));
         sh.mid_ray[qg * 3 + 0] = r.x; sh.mid_ray[qg * 3 + 1] = r.y; sh.mid_ray[qg * 3 + 2] = r.z;
     }
-    __syncwarp();
 
-    PixelState<BWD> ps;
-    ps.T = 1.0f;
-    ps.C0 = ps.C1 = ps.C2 = 0.f;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     if constexpr (BWD) {
         float T_final = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f;
         if (inside) {
@@ -201,8 +210,9 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     // forward: next slot of this pixel in its blend log (element index into blend_rec, +256 per blend; the host only
     // enables the log when the whole array can be indexed with 32 bits)
     uint32_t rec_idx = (uint32_t)tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)tid;
+    __syncthreads();  // barriers initialised, rays written (the only CTA barrier before the epilogue)
 
-    // head queue: sorted by depth, hd[0] is the next to blend
+    // head queue: sorted by depth, hd[0] is the next to blend; hi = Gaussian id
     float hd[HEAD], hs[HEAD];
     int hi[HEAD];
 #pragma unroll
@@ -220,15 +230,15 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         const int id = hi[0];
         if constexpr (!BWD) {
             const float alpha = hs[0];
-            const float test_T = fmul(ps.T, fsub(1.0f, alpha));
+            const float test_T = fmul(T, fsub(1.0f, alpha));
             if (test_T < kTThreshold) {
                 active = false;
                 return;
             }
-            ps.C0 = ffma(fmul(__ldg(colors + 3 * id + 0), alpha), ps.T, ps.C0);
-            ps.C1 = ffma(fmul(__ldg(colors + 3 * id + 1), alpha), ps.T, ps.C1);
-            ps.C2 = ffma(fmul(__ldg(colors + 3 * id + 2), alpha), ps.T, ps.C2);
-            ps.T = test_T;
+            C0 = ffma(fmul(__ldg(colors + 3 * id + 0), alpha), T, C0);
+            C1 = ffma(fmul(__ldg(colors + 3 * id + 1), alpha), T, C1);
+            C2 = ffma(fmul(__ldg(colors + 3 * id + 2), alpha), T, C2);
+            T = test_T;
             if (a.blend_rec != nullptr) {
                 // streaming store: the log is written once and read by the backward pass much later
                 const uint32_t rec_end = ((uint32_t)tile_lin + 1u) * (uint32_t)a.rec_cap * 256u;
@@ -239,23 +249,23 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             const float G = hs[0];
             const float4 co = __ldg(conic_opacity + id);
             const float alpha = fminf(0.99f, fmul(co.w, G));
-            const float test_T = fmul(ps.T, fsub(1.0f, alpha));
+            const float test_T = fmul(T, fsub(1.0f, alpha));
             if (test_T < kTThreshold) {
                 active = false;
                 return;
             }
             const float2 xy = __ldg(means2D + id);
             const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
-            const float dchannel_dcolor = alpha * ps.T;
+            const float dchannel_dcolor = alpha * T;
             const float c0 = __ldg(colors + 3 * id + 0), c1 = __ldg(colors + 3 * id + 1), c2 = __ldg(colors + 3 * id + 2);
-            ps.C0 += c0 * alpha * ps.T;
-            ps.C1 += c1 * alpha * ps.T;
-            ps.C2 += c2 * alpha * ps.T;
+            C0 += c0 * alpha * T;
+            C1 += c1 * alpha * T;
+            C2 += c2 * alpha * T;
             const float inv_T = 1.0f / test_T;
             const float g0 = pc[0], g1 = pc[256], g2 = pc[512];
-            float dL_dalpha = (c0 - (pc[768] - ps.C0) * inv_T) * g0 + (c1 - (pc[1024] - ps.C1) * inv_T) * g1 +
-                              (c2 - (pc[1280] - ps.C2) * inv_T) * g2;
-            dL_dalpha *= ps.T;
+            float dL_dalpha = (c0 - (pc[768] - C0) * inv_T) * g0 + (c1 - (pc[1024] - C1) * inv_T) * g1 +
+                              (c2 - (pc[1280] - C2) * inv_T) * g2;
+            dL_dalpha *= T;
             dL_dalpha += (-pc[1536] / (1.f - alpha)) * pc[1792];
             const float dL_dG = co.w * dL_dalpha;
             const float gdx = G * dx, gdy = G * dy;
@@ -264,7 +274,7 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             accumulate_grads(ab.grad_accum, id, dchannel_dcolor * g0, dchannel_dcolor * g1, dchannel_dcolor * g2,
                              dL_dG * dG_ddelx * ddelx_dx, dL_dG * dG_ddely * ddely_dy, -0.5f * gdx * dx * dL_dG,
                              -0.5f * gdx * dy * dL_dG, -0.5f * gdy * dy * dL_dG, G * dL_dalpha);
-            ps.T = test_T;
+            T = test_T;
         }
 #pragma unroll
         for (int k = 1; k < HEAD; ++k) {
@@ -275,103 +285,49 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         hd[HEAD - 1] = kFltMax;
     };
 
-    // ---- an entry arrives at the pixel (front4OneFromMid inner body, :421-536) ---------------------------------------------
-    // Split in two so that the four entries a quad receives together can be evaluated with instruction-level
-    // parallelism: head_eval is side-effect free (alpha test first, then -- only for survivors -- the 48-byte
-    // inverse covariance and the depth on the pixel's ray); head_insert is the sequential queue update.
-    // Entries flagged kDeadBit cannot reach any pixel of this 4x4 block (conservative test at the tail stage):
-    // they still flow through every queue (they decide WHEN other entries are popped and blended) but are never
-    // evaluated per pixel.
-    auto head_eval = [&](int id, float& ed, float& es) -> bool {
-        if (id < 0 || (id & kDeadBit) || !active) return false;
-        const float2 xy = __ldg(means2D + id);
-        const float4 co = __ldg(conic_opacity + id);
-        const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
-        const float power = gaussian_power(dx, dy, co.x, co.y, co.z);
-        if (power > 0.0f) return false;
-        const float G = expf(power);
-        const float alpha = fminf(0.99f, fmul(co.w, G));
-        if (alpha < kAlphaThreshold) return false;
-        float ic[6], ux, uy, uz;
-        load_inv(cov3D_inv, id, ic, ux, uy, uz);
-        const Vec3 ray{sh.pix_ray[tid], sh.pix_ray[256 + tid], sh.pix_ray[512 + tid]};
-        ed = depth_along_ray(ic, ux, uy, uz, ray);
-        es = BWD ? G : alpha;
-        return !(ed < 0.0f);
-    };
-    auto head_insert = [&](bool ok, int id, float ed, float es) {
-        if (hcount >= HEAD) blend_one();
-        if (!ok || !active) return;
-        int ei = id;
-#pragma unroll
-        for (int k = 0; k < HEAD; ++k) {
-            if (ed < hd[k]) {
-                const float td = hd[k], ts = hs[k];
-                const int ti = hi[k];
-                hd[k] = ed; hs[k] = es; hi[k] = ei;
-                ed = td; es = ts; ei = ti;
-            }
-        }
-        ++hcount;
+    // ---- per-quad stream ring and the pixel's reader state --------------------------------------------------------------
+    int* const rq = sh.ring + qg * kRing;
+    uint32_t wr = 0;       // entries appended to my quad's ring so far (identical in the 4 lanes of the quad)
+    uint32_t cursor = 0;   // entries of it this pixel has looked at
+    int held = -1;         // list position of a survivor of the alpha test that waits for the insertion step
+    float held_s = 0.f;    // its alpha (forward) / G (backward)
+    // free ring entries of my quad: a slot is reusable once every pixel of the quad that still blends has read it
+    auto ring_free = [&]() -> int {
+        uint32_t behind = active ? wr - cursor : 0u;
+        behind = max(behind, __shfl_xor_sync(0xffffffffu, behind, 1));
+        behind = max(behind, __shfl_xor_sync(0xffffffffu, behind, 2));
+        return kRing - (int)behind;
     };
 
     // ---- mid queue of this quad ---------------------------------------------------------------------------------------
     float* const md = sh.mid_d + qg * Sh::kMidStride;
     int* const mi = sh.mid_id + qg * Sh::kMidStride;
-    int* const oi = sh.out_id + qg * 4;
     int mcount = 0, mbase = 0;  // resident entries live at md[mbase .. mbase+mcount)
 
-    // the 4 smallest mid entries (already in oi[0..3]) go to the 4 pixels of the quad
-    auto quad_to_head = [&]() {
-        const bool any = __any_sync(qmask, active);
-        if (!any) return;
-        int ids[4];
-        float ed[4], es[4];
-        bool ok[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ids[k] = oi[k];
-#if STP_HIER_SPEC
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ok[k] = head_eval(ids[k], ed[k], es[k]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) head_insert(ok[k], ids[k], ed[k], es[k]);
-#else
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (hcount >= HEAD) blend_one();
-            ok[k] = head_eval(ids[k], ed[k], es[k]);
-            if (ok[k]) {
-                float e_d = ed[k], e_s = es[k];
-                int ei = ids[k];
-#pragma unroll
-                for (int j = 0; j < HEAD; ++j) {
-                    if (e_d < hd[j]) {
-                        const float td = hd[j], ts = hs[j];
-                        const int ti = hi[j];
-                        hd[j] = e_d; hs[j] = e_s; hi[j] = ei;
-                        e_d = td; e_s = ts; ei = ti;
-                    }
-                }
-                ++hcount;
-            }
-        }
-#endif
+    int* const po = sh.popped + qg * 4;
+    // po[0..3] (the four entries that just left the mid queue, in order) -> the quad's ring, live entries only
+    auto append_popped = [&]() {
+        const int e = po[p];
+        const bool live = (e & kDeadBit) == 0;
+        const uint32_t lm = (__ballot_sync(qmask, live) >> (lane & ~3)) & 0xfu;
+        if (live) rq[(wr + (uint32_t)__popc(lm & ((1u << p) - 1u))) & (kRing - 1)] = e;
+        wr += (uint32_t)__popc(lm);
+        __syncwarp(qmask);
     };
-
-    // one group of 4 tail entries (ids g_id[0..3], quad lane p owns entry p) enters the mid queue (:566-677)
-    // depth of one tail entry on the quad's ray (side-effect free: the four groups of a tail pop are evaluated
-    // together for instruction-level parallelism, then merged one after the other)
-    auto mid_depth = [&](int my_id) -> float {
+    // depth of one tail entry on the quad's ray
+    auto mid_depth = [&](int my_e) -> float {
         float my_d = kFltMax;
-        if (my_id >= 0) {
+        if (my_e >= 0) {
             float ic[6], ux, uy, uz;
-            load_inv(cov3D_inv, my_id & kIdMask, ic, ux, uy, uz);
+            slab_ldg_inv(slab, first + (uint32_t)(my_e & kIdxMask), ic, ux, uy, uz);
             const Vec3 mr{sh.mid_ray[qg * 3], sh.mid_ray[qg * 3 + 1], sh.mid_ray[qg * 3 + 2]};
             my_d = depth_along_ray(ic, ux, uy, uz, mr);
         }
         return my_d;
     };
-    auto mid_push_group = [&](int my_id, float my_d) {
+    // one group of 4 tail entries (quad lane p owns entry p) enters the mid queue (:566-677); the 4 smallest leave for the
+    // quad's stream ring when the queue would hold more than MID-4
+    auto mid_push_group = [&](int my_e, float my_d) {
         // rank among the 4 new entries, ties by lane (shflRankingLocal, :129-143)
         float nd[4];
         int rank = 0;
@@ -399,11 +355,17 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         __syncwarp(qmask);
         const bool pop = mcount + 4 > MID - 4;
         const int shift = pop ? 4 : 0;
+        // the popped four, by rank, pass through `po` so that entries no pixel of the block will ever evaluate (dead bit,
+        // padding) can be left out of the stream: they had to flow through the queues, the pixels need not see them
+        // (with 4x4 culling nothing dead ever enters the queues: the popped four go straight to the ring)
+        int* const out = CULL ? rq : po;
+        const uint32_t obase = CULL ? wr : 0u;
+        constexpr uint32_t omask = CULL ? (uint32_t)(kRing - 1) : 3u;
         if (pos_new >= shift) {
             md[pos_new - shift] = my_d;
-            mi[pos_new - shift] = my_id;
+            mi[pos_new - shift] = my_e;
         } else {
-            oi[pos_new] = my_id;
+            out[(obase + (uint32_t)pos_new) & omask] = my_e;
         }
 #pragma unroll
         for (int j = 0; j < Sh::kMidCap / 4; ++j) {
@@ -411,14 +373,16 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
                 md[rpos[j] - shift] = rd[j];
                 mi[rpos[j] - shift] = ri[j];
             } else if (rpos[j] >= 0) {
-                oi[rpos[j]] = ri[j];
+                out[(obase + (uint32_t)rpos[j]) & omask] = ri[j];
             }
         }
         mbase = 0;
         mcount = mcount + 4 - shift;
+        if constexpr (CULL) wr += (uint32_t)shift;
         __syncwarp(qmask);
-        if (pop) quad_to_head();
-        __syncwarp(qmask);
+        if constexpr (!CULL) {
+            if (pop) append_popped();
+        }
     };
 
     // ---- tail queue of this block -------------------------------------------------------------------------------------
@@ -427,76 +391,65 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     float* const nwd = sh.new_d + b * 48;
     int* const nwi = sh.new_id + b * 48;
     int tcount = 0, tbase = 0;  // resident entries live at td[tbase .. tbase+tcount)
+    const Vec3 tray{sh.tail_ray[b * 3], sh.tail_ray[b * 3 + 1], sh.tail_ray[b * 3 + 2]};
 
-    // tail -> mid hand-over queue of this block (ids only, groups of 4); fhead / fcount are identical in the 16 lanes
-    int* const ff = sh.fifo_id + b * kFifoIds;
-    int fhead = 0, fcount = 0;
-    // process queued groups while both blocks of the warp have one (convergent), or while a backlog exceeds `limit`
-    auto consume = [&](int limit) {
-        while (true) {
-            if (!__any_sync(hmask, active)) fcount = 0;  // nothing downstream of this block is listening any more
-            const uint32_t hv = __ballot_sync(0xffffffffu, fcount > 0);
-            if (hv == 0) break;
-            const bool both = (hv & 0xffffu) != 0 && (hv >> 16) != 0;
-            if (!both && !__any_sync(0xffffffffu, fcount > limit)) break;
-            if (fcount > 0) {
-                const int id_g = ff[(fhead * 4 + p) & (kFifoIds - 1)];
-                mid_push_group(id_g, mid_depth(id_g));
-                fhead = (fhead + 1) & (kFifoGroups - 1);
-                --fcount;
-            }
-            __syncwarp();
-        }
-    };
-
-    const uint2 range = ranges[tile_y * f.grid_x + tile_x];
-    for (uint32_t progress = range.x; progress < range.y; progress += 32) {
-        if (!__any_sync(0xffffffffu, active)) break;  // per-warp early exit (:692)
-
+    // batch k of the tile list: 32 records from the slab ring -> tail queue of both blocks of this warp -> pops -> mid
+    auto tail_batch = [&](int k, bool block_alive) {
+        const int s = k % kStages;
+        mbar_wait(&sh.full[s], (uint32_t)(k / kStages) & 1u);
+        const float4* const stage = sh.slab[s];
         // each lane of the half-warp evaluates 2 of the 32 new entries on the block-centre ray
         float e_d[2];
         int e_id[2];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const uint32_t src = progress + hl + 16 * s;
-            int id = -1;
+        for (int t = 0; t < 2; ++t) {
+            const int slot = hl + 16 * t;
+            const int src = k * kBatch + slot;  // tile-local list position
+            int e = -1;
             float d = kFltMax;
-            if (src < range.y) id = (int)__ldg(point_list + src);
-            if (id >= 0) {
-                const float2 xy = __ldg(means2D + id);
-                const float4 co = __ldg(conic_opacity + id);
+            if (src < n && block_alive) {
+                const uint32_t j = first + (uint32_t)src;
+                float4 c0, c1;
+                slab_load_head(stage + 4 * slot, j, c0, c1);
+                const float2 xy = make_float2(c0.x, c0.y);
+                const float4 co = make_float4(c0.z, c0.w, c1.x, c1.y);
                 // conservative "cannot reach this block" test (bounding box of the alpha >= 1/255 ellipse, inflated far
                 // beyond the rounding error of the exact evaluations below and per pixel)
                 bool unreachable = false;
-                if constexpr (!CULL || STP_HIER_PREFILTER) unreachable = block_unreachable(xy, co, (float)cx, (float)cy);
+                if constexpr (!CULL) unreachable = block_unreachable(xy, co, (float)cx, (float)cy);
                 bool culled = false;
-                if constexpr (CULL) {  // :723-743; an unreachable entry is always rejected by the exact test as well
-                    culled = unreachable;
-                    if (!culled) {
-                        float mx, my;
-                        const float pw = max_contrib_power<3, 3>(co.x, co.y, co.z, xy.x, xy.y, (float)cx, (float)cy,
-                                                                 fadd((float)cx, 3.0f), fadd((float)cy, 3.0f), mx, my);
-                        culled = fminf(0.99f, fmul(co.w, expf(-pw))) < kAlphaThreshold;
-                    }
+                if constexpr (CULL) {  // :723-743
+                    float mx, my;
+                    const float pw = max_contrib_power<3, 3>(co.x, co.y, co.z, xy.x, xy.y, (float)cx, (float)cy,
+                                                             fadd((float)cx, 3.0f), fadd((float)cy, 3.0f), mx, my);
+                    culled = (-pw < kPowerReject && co.w <= 1.0f) || fminf(0.99f, fmul(co.w, expf(-pw))) < kAlphaThreshold;
                 }
                 if (!culled) {
-                    float ic[6], ux, uy, uz;
-                    load_inv(cov3D_inv, id, ic, ux, uy, uz);
-                    const Vec3 tray{sh.tail_ray[b * 3], sh.tail_ray[b * 3 + 1], sh.tail_ray[b * 3 + 2]};
-                    d = depth_along_ray(ic, ux, uy, uz, tray);
-                    if (!CULL && unreachable) id |= kDeadBit;
-                } else {
-                    id = -1;
+                    float4 c2, c3;
+                    slab_load_tail(stage + 4 * slot, j, c2, c3);
+                    const float ic[6] = {c1.w, c2.x, c2.y, c2.z, c2.w, c3.x};
+                    d = depth_along_ray(ic, c3.y, c3.z, c3.w, tray);
+                    e = (!CULL && unreachable) ? (src | kDeadBit) : src;
                 }
             }
-            e_d[s] = d;
-            e_id[s] = (d == kFltMax) ? -1 : id;
+            e_d[t] = d;
+            e_id[t] = (d == kFltMax) ? -1 : e;
+        }
+        // this warp is done with the stage: the last of the eight warps re-arms it with batch k + kStages
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&sh.released[s], 1u) == kWarps - 1) {
+                sh.released[s] = 0u;
+                __threadfence_block();
+                if (k + kStages < nb) request_batch(k + kStages);
+            }
         }
         // with 4x4 culling only a few of the 32 entries survive: compact them (list order kept) into new_d/new_id so
         // that every later step costs O(valid) instead of O(32)
         constexpr bool COMPACT = CULL && STP_HIER_COMPACT;
-        const uint32_t vm0 = __ballot_sync(hmask, e_id[0] >= 0) >> (half * 16);
-        const uint32_t vm1 = __ballot_sync(hmask, e_id[1] >= 0) >> (half * 16);
+        const uint32_t vm0 = __ballot_sync(0xffffffffu, e_id[0] >= 0) >> (half * 16) & 0xffffu;
+        const uint32_t vm1 = __ballot_sync(0xffffffffu, e_id[1] >= 0) >> (half * 16) & 0xffffu;
         const int n0 = __popc(vm0), n_valid = n0 + __popc(vm1);
         int cpos[2] = {hl, hl + 16};
         if constexpr (COMPACT) {
@@ -504,20 +457,20 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             cpos[1] = n0 + __popc(vm1 & ((1u << hl) - 1u));
         }
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            if (!COMPACT || e_id[s] >= 0) {
-                nwd[cpos[s]] = e_d[s];
-                nwi[cpos[s]] = e_id[s];
+        for (int t = 0; t < 2; ++t) {
+            if (!COMPACT || e_id[t] >= 0) {
+                nwd[cpos[t]] = e_d[t];
+                nwi[cpos[t]] = e_id[t];
             }
         }
         // my resident entries (positions hl, hl+16 of the resident run) before anything is overwritten
         float r_d[2];
         int r_id[2];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int k = hl + 16 * s;
-            r_d[s] = (k < tcount) ? td[tbase + k] : kFltMax;
-            r_id[s] = (k < tcount) ? ti[tbase + k] : -1;
+        for (int t = 0; t < 2; ++t) {
+            const int kk = hl + 16 * t;
+            r_d[t] = (kk < tcount) ? td[tbase + kk] : kFltMax;
+            r_id[t] = (kk < tcount) ? ti[tbase + kk] : -1;
         }
         __syncwarp(hmask);
         // ranks: new entry i -> #new before it (depth, then list position) + #resident <= it;
@@ -528,9 +481,9 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             for (int j = 0; j < n_valid; ++j) {
                 const float dj = nwd[j];
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    rk_new[s] += (dj < e_d[s]) || (dj == e_d[s] && j < cpos[s]);
-                    sh_res[s] += dj < r_d[s];
+                for (int t = 0; t < 2; ++t) {
+                    rk_new[t] += (dj < e_d[t]) || (dj == e_d[t] && j < cpos[t]);
+                    sh_res[t] += dj < r_d[t];
                 }
             }
         } else {
@@ -554,99 +507,192 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             }
         }
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            if (e_id[s] >= 0) {
-                // binary search: number of resident entries with depth <= e_d[s]
+        for (int t = 0; t < 2; ++t) {
+            if (e_id[t] >= 0) {
+                // binary search: number of resident entries with depth <= e_d[t]
                 int lo = 0, hi_ = tcount;
                 while (lo < hi_) {
                     const int mid = (lo + hi_) >> 1;
-                    if (td[tbase + mid] <= e_d[s]) lo = mid + 1; else hi_ = mid;
+                    if (td[tbase + mid] <= e_d[t]) lo = mid + 1; else hi_ = mid;
                 }
-                rk_new[s] += lo;
+                rk_new[t] += lo;
             }
         }
         __syncwarp(hmask);
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            if (e_id[s] >= 0) {
-                td[rk_new[s]] = e_d[s];
-                ti[rk_new[s]] = e_id[s];
+        for (int t = 0; t < 2; ++t) {
+            if (e_id[t] >= 0) {
+                td[rk_new[t]] = e_d[t];
+                ti[rk_new[t]] = e_id[t];
             }
-            const int k = hl + 16 * s;
-            if (k < tcount) {
-                td[k + sh_res[s]] = r_d[s];
-                ti[k + sh_res[s]] = r_id[s];
+            const int kk = hl + 16 * t;
+            if (kk < tcount) {
+                td[kk + sh_res[t]] = r_d[t];
+                ti[kk + sh_res[t]] = r_id[t];
             }
         }
         tbase = 0;
         tcount += n_valid;
         __syncwarp(hmask);
 
-        // pop the 16 smallest while more than 32 are held (at most twice, :827-846).  The popped ids are handed to the
-        // mid stage through a per-block FIFO: which entries leave the tail, and in which order, does not depend on
-        // anything downstream, so the mid / head work of the two blocks of this warp can be deferred until BOTH have a
-        // group to process and then runs convergently (with 4x4 culling the two tails fill at different times; pushing
-        // each pop through mid and head at once would leave the other half-warp idle).
+        // pop the 16 smallest while more than 32 are held (at most twice, :827-846): four groups of 4 through the mid stage
 #pragma unroll 1
         for (int rep = 0; rep < 2; ++rep) {
             if (tcount > 32) {
-#if STP_HIER_FIFO
-                ff[((fhead + fcount) * 4 + hl) & (kFifoIds - 1)] = ti[tbase + hl];
-                fcount += 4;
-#else
 #pragma unroll 1
                 for (int g = 0; g < 4; ++g) {
-                    const int id_g = ti[tbase + 4 * g + p];
-                    mid_push_group(id_g, mid_depth(id_g));
+                    const int e_g = ti[tbase + 4 * g + p];
+                    mid_push_group(e_g, mid_depth(e_g));
                 }
-#endif
                 tbase += 16;
                 tcount -= 16;
             }
         }
-#if STP_HIER_FIFO
-        __syncwarp();
-        consume(kFifoLimit);
-#endif
-    }
+    };
 
-    // ---- drain: tail -> mid -> head (:855-925) ---------------------------------------------------------------------------
-    consume(-1);
-    const bool half_alive = __any_sync(hmask, active);
-    if (!half_alive) tcount = 0;
-    while (__any_sync(0xffffffffu, tcount > 0)) {
-        if (tcount > 0) {
-            const int did = p < tcount ? ti[tbase + p] : -1;
-            mid_push_group(did, mid_depth(did));
-            tbase += 4;
-            tcount -= min(tcount, 4);
+    // ---- the pixel consumes its quad's stream (front4OneFromMid inner body, :421-536) ------------------------------------
+    // scan: one ring entry per call, the alpha test only (xy + conic/opacity = first half of the record)
+    auto scan_one = [&]() {
+        const int e = rq[cursor & (kRing - 1)];
+        ++cursor;
+        if (e & kDeadBit) return;  // cannot reach this block (or padding, -1): flows through the queues, never evaluated
+        float4 c0, c1;
+        slab_ldg_head(slab, first + (uint32_t)e, c0, c1);
+        const float dx = fsub(c0.x, pxf), dy = fsub(c0.y, pyf);
+        const float power = gaussian_power(dx, dy, c0.z, c0.w, c1.x);
+        if (power > 0.0f) return;
+        // exp(power) < exp(-5.6) < 1/255: with an opacity of at most one the alpha test below fails whatever the rounding
+        if (power < kPowerReject && c1.y <= 1.0f) return;
+        const float G = expf(power);
+        const float alpha = fminf(0.99f, fmul(c1.y, G));
+        if (alpha < kAlphaThreshold) return;
+        held = e;
+        held_s = BWD ? G : alpha;
+    };
+    // insertion step for the held survivor: depth on the pixel's ray (second half of the record), blend the head minimum
+    // if the head is full, insert by strict '<'
+    auto insert_held = [&]() {
+        const uint32_t j = first + (uint32_t)held;
+        held = -1;
+        const float4* const rec = slab + 4 * (size_t)j;
+        const uint32_t sw = slab_swizzle(j);
+        const float4 c1 = __ldg(rec + (1 ^ sw)), c2 = __ldg(rec + (2 ^ sw)), c3 = __ldg(rec + (3 ^ sw));
+        const float ic[6] = {c1.w, c2.x, c2.y, c2.z, c2.w, c3.x};
+        const Vec3 ray{sh.pix_ray[tid], sh.pix_ray[256 + tid], sh.pix_ray[512 + tid]};
+        float e_d = depth_along_ray(ic, c3.y, c3.z, c3.w, ray);
+        if (e_d < 0.0f) return;
+        if (hcount >= HEAD) blend_one();
+        if (!active) return;
+        float e_s = held_s;
+        int ei = __float_as_int(c1.z);
+#pragma unroll
+        for (int k = 0; k < HEAD; ++k) {
+            if (e_d < hd[k]) {
+                const float td_ = hd[k], ts = hs[k];
+                const int ti_ = hi[k];
+                hd[k] = e_d; hs[k] = e_s; hi[k] = ei;
+                e_d = td_; e_s = ts; ei = ti_;
+            }
         }
-    }
-    if (!half_alive) mcount = 0;
-    while (__any_sync(0xffffffffu, mcount > 0)) {
-        if (mcount > 0) {
-            __syncwarp(qmask);
-            const int v = mi[mbase + p];
-            __syncwarp(qmask);
-            oi[p] = v;
-            __syncwarp(qmask);
-            mbase += 4;
-            mcount -= 4;
-            quad_to_head();
+        ++hcount;
+    };
+
+    // ---- the warp alternates between producing (tail batches -> mid -> rings) and consuming (pixels read their rings) ----
+    int k = 0;             // next batch
+    bool stream_end = false;
+    while (true) {
+        const uint32_t alive = __ballot_sync(0xffffffffu, active);
+        if (alive == 0u) break;
+        const bool block_alive = ((alive >> (half * 16)) & 0xffffu) != 0u;
+        if (!block_alive) {  // nothing downstream of this block listens any more
+            tcount = 0;
+            mcount = 0;
         }
+        // ---- produce --------------------------------------------------------------------------------------------------
+        while (true) {
+            const int fr = ring_free();
+            const uint32_t ok32 = __ballot_sync(0xffffffffu, fr >= 32 || !active);
+            const uint32_t ok4 = __ballot_sync(0xffffffffu, fr >= 4 || !active);
+            if (k < nb) {
+                if (ok32 != 0xffffffffu) break;
+                tail_batch(k, block_alive);
+                ++k;
+                continue;
+            }
+            // drain: tail -> mid -> rings (:855-925), four entries per step and quad
+            const bool room = ((ok4 >> (half * 16)) & 0xffffu) == 0xffffu;
+            bool did = false;
+            if (room && tcount > 0) {
+                const int did_e = p < tcount ? ti[tbase + p] : -1;
+                mid_push_group(did_e, mid_depth(did_e));
+                tbase += 4;
+                tcount -= min(tcount, 4);
+                did = true;
+            } else if (room && mcount > 0) {
+                __syncwarp(qmask);
+                po[p] = mi[mbase + p];
+                __syncwarp(qmask);
+                append_popped();
+                mbase += 4;
+                mcount -= 4;
+                did = true;
+            }
+            if (!__any_sync(0xffffffffu, did)) break;
+        }
+        stream_end = __all_sync(0xffffffffu, k >= nb && tcount == 0 && mcount == 0);
+        // ---- consume --------------------------------------------------------------------------------------------------
+        while (true) {
+#pragma unroll 1
+            for (int it = 0; it < STP_HIER_SCAN; ++it) {  // several ring entries per vote: most fail the alpha test
+                if (active && held < 0 && cursor != wr) scan_one();
+            }
+            const uint32_t ready = __ballot_sync(0xffffffffu, active && held >= 0);
+            const uint32_t scan = __ballot_sync(0xffffffffu, active && held < 0 && cursor != wr);
+            if (ready == 0u && scan == 0u) break;
+            if (__popc(ready) >= STP_HIER_THRESH) {
+                if (active && held >= 0) insert_held();
+            } else if (scan == 0u) {
+                // nobody can scan any further and only a few lanes hold a survivor: they keep it for the next round unless
+                // the stream has ended or the producer needs the ring space their cursors pin
+                bool flush = stream_end;
+                if (!flush) {
+                    const int fr = ring_free();
+                    flush = !__all_sync(0xffffffffu, fr >= 32 || !active);
+                }
+                if (!flush) break;
+                if (active && held >= 0) insert_held();
+            }
+        }
+        if (stream_end && !__any_sync(0xffffffffu, active && (held >= 0 || cursor != wr))) break;
     }
     while (active && hcount > 0) blend_one();
 
     if constexpr (!BWD) {
         if (inside) {
-            a.final_T[pix_id] = ps.T;
-            a.out_color[pix_id] = ffma(ps.T, f.background[0], ps.C0);
-            a.out_color[plane + pix_id] = ffma(ps.T, f.background[1], ps.C1);
-            a.out_color[2 * plane + pix_id] = ffma(ps.T, f.background[2], ps.C2);
+            a.final_T[pix_id] = T;
+            a.out_color[pix_id] = ffma(T, f.background[0], C0);
+            a.out_color[plane + pix_id] = ffma(T, f.background[1], C1);
+            a.out_color[2 * plane + pix_id] = ffma(T, f.background[2], C2);
             if (a.blend_rec != nullptr) {
                 const uint32_t nrec = (rec_idx - ((uint32_t)tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)tid)) >> 8;
                 a.blend_count[pix_id] = nrec;
                 if (nrec > (uint32_t)a.rec_cap) atomicOr(a.tile_flags + tile_lin, 1u);
+            }
+        }
+    }
+
+    // ---- leave the slab ring in order: a warp that stops early still has to release every remaining batch (the other
+    // warps' refills wait for all eight), and no bulk copy may be in flight when the CTA exits -----------------------------
+    for (; k < nb; ++k) {
+        const int s = k % kStages;
+        mbar_wait(&sh.full[s], (uint32_t)(k / kStages) & 1u);
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&sh.released[s], 1u) == kWarps - 1) {
+                sh.released[s] = 0u;
+                __threadfence_block();
+                if (k + kStages < nb) request_batch(k + kStages);
             }
         }
     }

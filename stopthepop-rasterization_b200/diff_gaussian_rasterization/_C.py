@@ -251,11 +251,14 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
                                  pixel_colors, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
                                  imageBuffer, settings_dict, debug, tile_band=None, want_param_slab=False,
                                  sync_group=None, sync_chunks=4):
-    """sync_group (ours only): a torch.distributed process group over which the five PARAMETER gradients are summed
-    before they are returned (data-parallel training: views or tile bands sharded across GPUs).  The exchange is
-    overlapped with the computation: the preprocess-backward stage runs in `sync_chunks` ranges of Gaussians and the
-    all-reduce of each range's SH-gradient rows (81 % of the bytes) starts on a side stream as soon as the range is
-    done; only the last range and the small arrays remain exposed."""
+    """sync_group (ours only): a torch.distributed process group over which the gradients are summed before they are
+    returned (data-parallel training: views or tile bands sharded across GPUs).
+    Views (no tile_band): the five PARAMETER gradients are all-reduced, overlapped with the computation: the
+    preprocess-backward stage runs in `sync_chunks` ranges of Gaussians and the all-reduce of each range's SH-gradient
+    rows (81 % of the bytes) starts on a side stream as soon as the range is done; only the last range and the small
+    arrays remain exposed.
+    Tile bands (tile_band given): the packed screen-space accumulator (48 B/Gaussian) is all-reduced between the two
+    backward stages instead (_backward_band_exchange); all eight returned gradients are then the full-frame ones."""
     device = means3D.device
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)  # rasterize_points.cu:169-170
@@ -294,6 +297,8 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
         with torch.cuda.device(device):
             if sync_group is None:
                 rc = _lib.stp_backward(*args)
+            elif tile_band is not None:
+                rc = _backward_band_exchange(args, P, grad_accum, sync_group)
             else:
                 rc = _backward_overlapped(args, P, M, dL_dsh, flat[offs[1]:offs[5]], sync_group,
                                           int(sync_chunks), device)
@@ -348,6 +353,20 @@ def _backward_overlapped(args, P, M, dL_dsh, small, group, chunks, device):
         dist.all_reduce(small, group=group)
     main.wait_stream(comm)
     return 0
+
+
+def _backward_band_exchange(args, P, grad_accum, group):
+    """tile-band sharding (one view, bands of tile rows per rank): the per-Gaussian backward is linear in the packed
+    screen-space gradients, and every rank holds the geometry state of every visible Gaussian (visibility does not
+    depend on the band, preprocess.cu), so the ONE exchange is an all-reduce of the 48 B/Gaussian accumulator between
+    the render-backward and the preprocess-backward stage -- 5x less than the 236 B/Gaussian of parameter gradients
+     -- after which every rank finishes the same preprocess-backward and holds the full gradients."""
+    import torch.distributed as dist
+    rc = _lib.stp_backward_render(*args)
+    if rc != 0:
+        return rc
+    dist.all_reduce(grad_accum, group=group)
+    return _lib.stp_backward_preprocess(*args, 0, P)
 
 
 def blend_record_cap_of(imageBuffer, W, H):

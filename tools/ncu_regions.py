@@ -28,7 +28,8 @@ for spec in regs.split(","):
     name, ab = spec.split(":")
     a, b = [int(x) for x in ab.split("-")]
     s = sum(v[0] for (f, l), v in data.items() if f == fname and a <= l <= b)
-    print(f"{name:28s} {100*s/tot:5.1f}%")
+    t = sum(v[1] for (f, l), v in data.items() if f == fname and a <= l <= b)
+    print(f"{name:28s} {100*s/tot:5.1f}%   lanes/instr {t/max(s,1):5.1f}")
 files = sorted({f for f, _ in data})
 for f in files:
     s = sum(v[0] for (ff, l), v in data.items() if ff == f)
