@@ -141,6 +141,20 @@ static void view_ray(const OrcInputs* in, float pxl, float pyl, float* d) {
     const float inv = 1.0f / sqrtf(fmaf(vz, vz, fmaf(vx, vx, vy * vy)));
     d[0] = vx * inv; d[1] = vy * inv; d[2] = vz * inv;
 }
+/* the same ray as compiled inside renderSortedFullCUDA (resorted_render.cuh:521-533): the pixel is the pair of loop
+ * counters x (outer) / y (inner), the x products leave the inner loop before FMA contraction, so the unprojection is
+ * m3 + fma(m1, ny, m0 * nx) -- one rounding away from view_ray; pinned at 4K against the reference build
+ * (tests/test_gpu_matrix.py::test_full_sort_at_benchmark_size_matches_reference_build). */
+static void view_ray_xloop(const OrcInputs* in, float pxl, float pyl, float* d) {
+    const float* m = in->inv_viewproj;
+    const float nx = fmaf(pxl, 2.0f / (float)in->W, -1.0f), ny = fmaf(pyl, 2.0f / (float)in->H, -1.0f);
+    const float pw = m[15] + fmaf(m[7], ny, m[3] * nx), pz = m[14] + fmaf(m[6], ny, m[2] * nx);
+    const float py = m[13] + fmaf(m[5], ny, m[1] * nx), px = m[12] + fmaf(m[4], ny, m[0] * nx);
+    const float rw = 1.0f / pw;
+    const float vx = fmaf(px, rw, -in->campos[0]), vy = fmaf(py, rw, -in->campos[1]), vz = fmaf(pz, rw, -in->campos[2]);
+    const float inv = 1.0f / sqrtf(fmaf(vz, vz, fmaf(vx, vx, vy * vy)));
+    d[0] = vx * inv; d[1] = vy * inv; d[2] = vz * inv;
+}
 /* depthAlongRay, stopthepop_common.cuh:43-55; ic = cov3D_inv row of 12 floats */
 static void depth_parts(const float* ic, const float* d, float* num, float* rcp) {
     const float vx = dot3c(ic[0], d[0], ic[1], d[1], ic[2], d[2]);
@@ -765,7 +779,7 @@ static void render_full(const OrcInputs* in, OrcState* st, BwdCtx* bwd) {
         const int px = pid % W, py = pid / W;
         const uint32_t* rg = st->ranges + 2 * ((py / 16) * gx + px / 16);
         const int n = (int)(rg[1] - rg[0]), rounds = (n + 255) / 256;
-        float ray[3]; view_ray(in, (float)px, (float)py, ray);
+        float ray[3]; view_ray_xloop(in, (float)px, (float)py, ray);
         FS win[1024]; /* blocked arrangement: thread t, item i -> win[4t+i] */
         for (int t = 0; t < 256; ++t)
             for (int i = 0; i < 3; ++i) {

@@ -437,7 +437,7 @@ render_full_fast_kernel(Frame f, RenderArgs a) {
         if (!(px < (uint32_t)f.W)) break;  // warp-uniform
         const uint32_t pix_id = (uint32_t)f.W * py + px;
         const float pxf = (float)px, pyf = (float)py;
-        const Vec3 ray = view_ray(cam, pxf, pyf);
+        const Vec3 ray = view_ray_xloop(cam, pxf, pyf);
         __syncwarp();  // the previous pixel's reads of this warp's shared-memory rows are complete
         int S = 0;
         for (int base = 0; base < n; base += 32) {
@@ -528,7 +528,7 @@ render_full_kernel(Frame f, RenderArgs a) {
         const uint32_t pix_id = (uint32_t)f.W * py + px;
         if (n <= 1024 && a.n_contrib[pix_id] != kSlowMark) continue;  // done by render_full_fast_kernel (warp-uniform)
         const float pxf = (float)px, pyf = (float)py;
-        const Vec3 ray = view_ray(cam, pxf, pyf);
+        const Vec3 ray = view_ray_xloop(cam, pxf, pyf);
 
         float k[32];
         int v[32];

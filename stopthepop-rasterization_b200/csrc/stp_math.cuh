@@ -241,6 +241,29 @@ STP_DEV Vec3 view_ray(const RayCam& rc, float pix_x, float pix_y) {
     return d;
 }
 
+// The same ray as compiled inside renderSortedFullCUDA (resorted_render.cuh:521-533), where the pixel is not the thread's
+// own but the pair of loop counters x (outer) / y (inner): the x-dependent products are loop invariant and leave the
+// inner loop BEFORE the multiply-adds are contracted, so the unprojection is  i3 + fma(i1, ny, i0 * nx)  instead of
+// i3 + fma(i0, nx, i1 * ny).  One rounding apart -- enough to flip the order of two Gaussians whose depths along the
+// ray agree to a few ulps (a handful of pixels at 4K).
+STP_DEV Vec3 view_ray_xloop(const RayCam& rc, float pix_x, float pix_y) {
+    const float nx = ffma(pix_x, rc.two_over_w, -1.0f);
+    const float ny = ffma(pix_y, rc.two_over_h, -1.0f);
+    const float pw = fadd(rc.i3[3], ffma(rc.i1[3], ny, fmul(rc.i0[3], nx)));
+    const float pz = fadd(rc.i3[2], ffma(rc.i1[2], ny, fmul(rc.i0[2], nx)));
+    const float py = fadd(rc.i3[1], ffma(rc.i1[1], ny, fmul(rc.i0[1], nx)));
+    const float px = fadd(rc.i3[0], ffma(rc.i1[0], ny, fmul(rc.i0[0], nx)));
+    const float rw = frcp(pw);
+    const float vx = ffma(px, rw, -rc.cx), vy = ffma(py, rw, -rc.cy), vz = ffma(pz, rw, -rc.cz);
+    const float len2 = ffma(vz, vz, ffma(vx, vx, fmul(vy, vy)));
+    const float inv = fdiv(1.0f, fsqrt(len2));
+    Vec3 d;
+    d.x = fmul(vx, inv);
+    d.y = fmul(vy, inv);
+    d.z = fmul(vz, inv);
+    return d;
+}
+
 // depthAlongRay (stopthepop_common.cuh:43-55): numerator and reciprocal denominator kept separate
 // because one caller fuses the final product with "+ 8" (per-tile depth key).
 //   ic = {i00,i01,i02, i11,i12,i22},  u = Sigma^-1 (mu - o)

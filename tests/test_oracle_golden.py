@@ -143,3 +143,77 @@ def test_oracle_full_sort_backward_extension():
             lo_hi.append(float((oo.out_color.astype(np.float64) * dL).sum()))
         fd = (lo_hi[0] - lo_hi[1]) / (2 * eps)
         assert abs(fd - g[i]) <= 2e-2 * abs(g[i]), (i, fd, g[i])
+
+
+def test_oracle_hier_cull_fd_all_parameter_groups(golden):
+    """The StopThePop preset's backward (HIER + hierarchical_4x4_culling) cannot be pinned on the reference build (its
+    gradient is corrupted by a race, profiles/r01_reference_hier_cull_bwd_race.txt), so the oracle -- the checker of
+    the CUDA path for that configuration -- is pinned here by central finite differences of its reference-exact
+    forward over FIVE parameter groups (opacity, means3D, scales, rotations, SH-DC): directional derivatives along the
+    analytic gradient for the Gaussians with the largest gradient of each group.  The pipeline is only piecewise
+    smooth (sort order, alpha / transmittance thresholds, float32 images), so a probe only counts when the central
+    differences at step h and h/2 agree with each other within 1 % (the usual consistency filter), and at least 50
+    probes must pass in total (>= 5 per group).  Tolerances: the image is LINEAR in the SH-DC colour and the colour
+    touches no threshold, so that group must match to 0.2 % -- it pins the whole chain of blending weights (order,
+    alpha, transmittance) of this mode.  The other groups move the alpha >= 1/255 cut-off contour with the parameter;
+    the many small jumps at that contour add up to a smooth first-order term that no analytic backward (the
+    reference's included) contains -- measured 3-10 % for large faint Gaussians, largest for the scales, which move
+    the whole contour -- so opacity is held to 8 % and the geometric groups to 15 %: enough to catch the class of error
+    seen in the reference (factor 16), not a statement about the contour term."""
+    from oracle import cpu_oracle as co
+    f = golden("hier_cull_only")
+    s = f.scene
+    dL = s["dL_dout"].astype(np.float64)
+    base = dict(means3D=s["means3D"].copy(), scales=s["scales"].copy(), rotations=s["rotations"].copy(),
+                opacities=s["opacities"].copy(), shs=f.shs().copy())
+
+    def forward(**over):
+        a = dict(base)
+        a.update(over)
+        return co.Oracle(f.settings, a["means3D"], a["scales"], a["rotations"], a["opacities"], a["shs"], f.deg,
+                         s["viewmatrix"], s["projmatrix"], s["inv_viewprojmatrix"], s["campos"], s["bg"],
+                         float(s["tanfovx"]), float(s["tanfovy"]), f.W, f.H)
+
+    def loss(**over):
+        o = forward(**over)
+        v = float((o.out_color.astype(np.float64) * dL).sum())
+        o.close()
+        return v
+    g = forward().backward(s["dL_dout"], f.fx["out_color"])
+    groups = [("opacities", g["dL_dopacity"].reshape(f.P, -1)), ("means3D", g["dL_dmeans3D"].reshape(f.P, -1)),
+              ("scales", g["dL_dscales"].reshape(f.P, -1)), ("rotations", g["dL_drot"].reshape(f.P, -1)),
+              ("shs", g["dL_dsh"][:, 0, :].reshape(f.P, -1))]
+
+    def central(name, i, direction, h):
+        vals = []
+        for sgn in (+1.0, -1.0):
+            arr = base[name].copy()
+            row = arr[i, 0, :] if name == "shs" else arr[i].reshape(-1)
+            new = (row.astype(np.float64) + sgn * h * direction).astype(np.float32)
+            if name == "shs":
+                arr[i, 0, :] = new
+            else:
+                arr[i] = new.reshape(arr[i].shape)
+            vals.append((loss(**{name: arr}), new.astype(np.float64)))
+        taken = (vals[0][1] - vals[1][1]) @ direction  # the step actually taken after rounding to float32
+        return (vals[0][0] - vals[1][0]) / taken
+
+    passed, worst = {}, 0.0
+    for name, grad in groups:
+        mag = np.linalg.norm(grad.astype(np.float64), axis=1)
+        ok = 0
+        for i in np.argsort(-mag)[:60]:
+            direction = grad[i].astype(np.float64) / mag[i]
+            h = {"opacities": 4e-3, "means3D": 8e-3 * float(base["scales"][i].max()),
+                 "scales": 4e-2 * float(base["scales"][i].min()), "rotations": 2.5e-2, "shs": 4e-2}[name]
+            d1, d2 = central(name, i, direction, h), central(name, i, direction, 0.5 * h)
+            if abs(d1 - d2) > 1e-2 * abs(d2):
+                continue  # straddles a discontinuity (or drowns in float32 noise): not a usable probe
+            err = abs(d2 - mag[i]) / mag[i]
+            worst = max(worst, err)
+            assert err <= {"shs": 2e-3, "opacities": 8e-2}.get(name, 0.15), (name, int(i), d1, d2, float(mag[i]))
+            ok += 1
+            if ok >= 14:
+                break
+        passed[name] = ok
+    assert sum(passed.values()) >= 50 and min(passed.values()) >= 5, (passed, worst)
