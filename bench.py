@@ -306,7 +306,7 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
             return _C.rasterize_gaussians(c.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e,
                                           c.viewmatrix, c.projmatrix, c.inv_viewprojmatrix, c.tanfovx, c.tanfovy, H, W,
                                           sc.shs, sc.sh_degree, c.campos, False, settings, False, dbg,
-                                          tile_band=band_box["band"])
+                                          tile_band=band_box["band"], async_forward=a.async_forward)
 
         def bwd(c, out, g, dbg=2):
             return _C.rasterize_gaussians_backward(c.bg, sc.means3D, out[2], sc.opacities, e, sc.scales, sc.rotations,
@@ -380,7 +380,8 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
         if a.impl == "ours":
             rs = GaussianRasterizationSettings(H, W, cam_c.tanfovx, cam_c.tanfovy, bg, 1.0, vm, pm, iv, sc.sh_degree, cp,
                                                False, ext_settings, False, False)
-            color, radii = GaussianRasterizer(rs, tile_band=band_box["band"], sync_group=sync_group)(
+            color, radii = GaussianRasterizer(rs, tile_band=band_box["band"], sync_group=sync_group,
+                                              async_forward=a.async_forward)(
                 m3, means2D, op, shs=sh, scales=scl, rotations=rot)
             if bands is not None:
                 color_full = SH.gather_image_bands(color.detach(), bands)
@@ -483,6 +484,9 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
                         "streams are done); Gaussian parameters (model state) resident"},
         "clocks": clocks,
     }
+    if a.impl == "ours":
+        res["config"]["forward"] = ("asynchronous (async_forward=True: num_rendered resolved lazily, no host<->device "
+                                    "synchronisation in the forward call)" if a.async_forward else "synchronous")
     if bands is not None:
         res["config"]["num_rendered_is"] = "rank 0's band only"
     if full_sort_ref:
@@ -568,6 +572,9 @@ def main():
     ap.add_argument("--bands", default="balanced", choices=["balanced", "equal"],
                     help="tile-row bands of equal instance count (from a warm-up frame) or of equal height")
     ap.add_argument("--points", type=int, default=0, help="override the number of Gaussians of the workload's scene")
+    ap.add_argument("--sync-forward", dest="async_forward", action="store_false",
+                    help="ours: wait for num_rendered inside every forward call (the reference's behaviour) instead of the "
+                         "asynchronous forward (GaussianRasterizer(async_forward=True): no host<->device synchronisation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations")
     ap.add_argument("--trace-steps", action="store_true", help="diagnostics: per-step times of every timed region")

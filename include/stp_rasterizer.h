@@ -92,7 +92,17 @@ typedef struct StpTileBand {
  *   radii      [P] i32     (written for every Gaussian; 0 = culled)
  *   num_rendered_out  HOST int: number of (tile,Gaussian) instances R (one stream sync, like
  *                     the reference's cudaMemcpy at rasterizer_impl.cu:317)
+ *   debug             bit 0: synchronise + check after every stage (the reference's debug=true); bit 1: record stage
+ *                     timings (stp_timing_summary); bit 2 = STP_FORWARD_ASYNC: do NOT synchronise.
+ * STP_FORWARD_ASYNC: num_rendered_out must then point to TWO ints of PINNED host memory that stay valid until the stream
+ * has passed the call: [0] receives R, [1] the device error flags (bit 0: prefiltered violation), both by an
+ * asynchronous copy.  The binning arena is sized from the largest R this device has seen (x1.5; stp_note_num_rendered /
+ * stp_set_num_rendered_hint) -- a device without history falls back to the synchronous path.  If the frame does not fit
+ * (R > stp_binning_capacity(size of the binning arena)), every kernel after the tile scan returns immediately, out_color
+ * is all zeros and the three arenas are invalid: the caller must check R once the stream has passed the call (before the
+ * backward pass at the latest) and repeat the frame -- diff_gaussian_rasterization/_C.py does that on first use of R.
  */
+#define STP_FORWARD_ASYNC 4
 int stp_forward(stp_alloc_fn geom_alloc, void* geom_user,
                 stp_alloc_fn binning_alloc, void* binning_user,
                 stp_alloc_fn image_alloc, void* image_user,
@@ -200,6 +210,11 @@ typedef struct StpImageView {
     uint32_t* n_contrib;  /* [W*H] u32 (GLOBAL / KBUFFER / PPX_FULL only, like the reference) */
     uint32_t* ranges;     /* [2*tiles] u32 (start,end) per tile */
 } StpImageView;
+
+/* high-water mark of R on the current device, which sizes the speculative / asynchronous binning arena:
+ * note = raise it to at least R (asynchronous callers report the R they resolved), set = overwrite it (0 = forget) */
+void stp_note_num_rendered(int R);
+void stp_set_num_rendered_hint(int R);
 
 size_t stp_geometry_bytes(int P, int requires_cov3D_inv);
 /* arena size for `capacity` instances (rounded up to a multiple of 64) under the given settings (the depth-resorting

@@ -263,6 +263,20 @@ int stp_requires_cov3D_inv(const StpSettings* s) {
     return s->sort_mode != STP_SORT_GLOBAL || s->sort_order == STP_ORDER_PTD_CENTER || s->sort_order == STP_ORDER_PTD_MAX;
 }
 
+void stp_set_num_rendered_hint(int R) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return;
+    g_last_R[dev].store(R > 0 ? (uint32_t)R : 0u, std::memory_order_relaxed);
+}
+
+void stp_note_num_rendered(int R) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices || R <= 0) return;
+    uint32_t cur = g_last_R[dev].load(std::memory_order_relaxed);
+    while ((uint32_t)R > cur && !g_last_R[dev].compare_exchange_weak(cur, (uint32_t)R, std::memory_order_relaxed)) {
+    }
+}
+
 size_t stp_geometry_bytes(int P, int inv) { return required<GeometryState>((size_t)P, inv != 0); }
 size_t stp_binning_bytes(int capacity, const StpSettings* settings) {
     const bool slab = settings != nullptr && settings->sort_mode != STP_SORT_GLOBAL;
@@ -378,25 +392,40 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     pa.prefiltered = prefiltered != 0;
     pa.radii = radii;
     STP_CUDA(launch_preprocess(pa, f, g, img.tile_count, s.tile_based_culling, stream), "preprocess");
-    STP_CUDA(launch_tile_scan(f, g, img, stream), "tile scan");
-    g_launches += 2;
-    timer.mark("Preprocess");
 
-    // The binning arena is sized by R, which is only known after the preprocess kernel.  While that kernel runs, the
-    // arena is requested speculatively for 1.25x the largest R this device has seen (the allocation callback goes
-    // through the caller's allocator, tens of microseconds).  The arena is carved for the CAPACITY that was allocated
-    // (stp_binning_capacity of its size -- what the backward pass re-derives), so a generous buffer changes nothing,
-    // and a too small one is simply requested again.
+    // The binning arena is sized by R, which is only known after the preprocess kernel + tile scan.  It is requested
+    // for 1.5x the largest R this device has seen, while those kernels run (the allocation callback goes through the
+    // caller's allocator, tens of microseconds), and carved for the CAPACITY that was allocated (stp_binning_capacity of
+    // its size -- what the backward pass re-derives).
+    //   synchronous (default): R is read back (one stream synchronisation, where the reference blocks too,
+    //     rasterizer_impl.cu:317); a too small arena is simply requested again before anything uses it.
+    //   asynchronous (debug & STP_FORWARD_ASYNC, only once the device has a history): nothing is read back here.  The
+    //     tile scan compares R with the capacity on the device; if the arena is too small every later kernel of the frame
+    //     returns at once, the image stays black, and the caller -- who finds R > capacity in num_rendered_out[0] once
+    //     the copy below has landed -- runs the frame again (diff_gaussian_rasterization/_C.py does, on first use of R).
     int dev = 0;
     cudaGetDevice(&dev);
     std::atomic<uint32_t>& last_R = g_last_R[dev >= 0 && dev < kMaxDevices ? dev : 0];
     const uint32_t seen = last_R.load(std::memory_order_relaxed);
     const bool slab = s.uses_slab();
-    size_t cap = seen ? binning_round_cap((size_t)seen + seen / 4 + 4096) : 0;
+    const bool async = (debug & STP_FORWARD_ASYNC) != 0 && seen != 0 && num_rendered_out != nullptr && !s.render_depth &&
+                       (debug & 1) == 0;
+    size_t cap = seen ? binning_round_cap((size_t)seen + seen / 2 + 4096) : 0;
+    STP_CUDA(launch_tile_scan(f, g, img, async ? (uint32_t)cap : 0xFFFFFFFFu, stream), "tile scan");
+    g_launches += 2;
+    timer.mark("Preprocess");
     char* bp = cap ? binning_alloc(binning_user, required<BinningState>(cap, slab)) : nullptr;
+    if (async && !bp) return fail(STP_ERR_ALLOC, "binning arena allocation failed");
 
     uint32_t R = 0;
-    {
+    if (async) {
+        // num_rendered_out[0] = R, [1] = error flags of the preprocess kernel; valid once the stream has passed this point
+        cudaError_t e = cudaMemcpyAsync(num_rendered_out, g.counters + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "num_rendered read-back");
+        e = cudaMemsetAsync(out_color, 0, sizeof(float) * 3 * (size_t)width * height, stream);  // an aborted frame is black
+        if (e != cudaSuccess) return cuda_fail(e, "num_rendered read-back");
+        R = (uint32_t)cap;  // launch decisions below only need "maybe non-empty"
+    } else {
         uint32_t rf[2] = {0, 0};  // counters[1] = R, counters[2] = error flags raised by the preprocess kernel
         cudaError_t e = cudaMemcpyAsync(rf, g.counters + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess) return cuda_fail(e, "num_rendered read-back");
@@ -405,15 +434,17 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
         R = rf[0];
         if (rf[1] & 1u)  // the reference traps here (auxiliary.h:226-233)
             return fail(STP_ERR_INVALID_ARGUMENT, "Point is filtered although prefiltered is set. This shouldn't happen!");
+        if (num_rendered_out) {
+            num_rendered_out[0] = (int)R;
+            if (debug & STP_FORWARD_ASYNC) num_rendered_out[1] = -2;  // asked for asynchronous, answered synchronously
+        }
+        if (R > seen) last_R.store(R, std::memory_order_relaxed);
+        if (bp == nullptr || (size_t)R > cap) {
+            cap = binning_round_cap((size_t)R);
+            bp = binning_alloc(binning_user, required<BinningState>(cap, slab));
+        }
+        if (!bp) return fail(STP_ERR_ALLOC, "binning arena allocation failed");
     }
-    if (num_rendered_out) *num_rendered_out = (int)R;
-    if (R > seen) last_R.store(R, std::memory_order_relaxed);
-
-    if (bp == nullptr || (size_t)R > cap) {
-        cap = binning_round_cap((size_t)R);
-        bp = binning_alloc(binning_user, required<BinningState>(cap, slab));
-    }
-    if (!bp) return fail(STP_ERR_ALLOC, "binning arena allocation failed");
     BinningState b = BinningState::from_chunk(bp, cap, slab);
 
     if (R > 0) {
@@ -442,6 +473,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     ra.blend_count = img.blend_count;
     ra.tile_flags = img.tile_flags;
     ra.log_overflow = g.counters + 4;
+    ra.abort_flag = async ? g.counters + kAbortFlag : nullptr;
     ra.rec_cap = s.rec_cap;
     if (s.sort_mode == STP_SORT_GLOBAL) {
         STP_CUDA(launch_render_global_fwd(f, ra, stream), "render (GLOBAL)");

@@ -78,6 +78,7 @@ template <bool TBC, int ORDER>
 __global__ void __launch_bounds__(256, STP_DUP_MINB)
 duplicate_kernel(int P, Frame f, GeometryState g, const int* __restrict__ radii, uint32_t* __restrict__ cursor,
                  uint64_t* __restrict__ bucket, uint32_t cap) {
+    if (g.counters[kAbortFlag] != 0u) return;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     constexpr bool NEED_CO = TBC || ORDER == 3;
@@ -192,7 +193,7 @@ constexpr int kLargeThreads = 1024;
 // tens of KB in L2, so a redundant read is cheaper than any inter-CTA dependency), then scans its own segment.
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(int tiles, const uint32_t* __restrict__ count, uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
-                 uint32_t* __restrict__ large_tiles, uint32_t* __restrict__ counters) {
+                 uint32_t* __restrict__ large_tiles, uint32_t* __restrict__ counters, uint32_t capacity) {
     __shared__ uint32_t s_warp[kScanThreads / 32];
     __shared__ uint32_t s_before;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -229,7 +230,12 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ count, uint2* __restric
         ranges[t] = c ? make_uint2(start, end) : make_uint2(0u, 0u);
         cursor[t] = start;
         if (c > (uint32_t)kSmallCap) large_tiles[atomicAdd(counters + 3, 1u)] = (uint32_t)t;
-        if (t == tiles - 1) counters[1] = end;  // R
+        if (t == tiles - 1) {
+            counters[1] = end;  // R
+            // asynchronous forward (api.cu): the binning arena was sized before R was known.  If it is too small every
+            // later kernel of this frame returns at once (kAbortFlag) and the host re-runs the frame when it looks at R.
+            counters[kAbortFlag] = end > capacity ? 1u : 0u;
+        }
     }
 }
 
@@ -344,6 +350,7 @@ tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                        const uint64_t* __restrict__ bucket, uint64_t* __restrict__ keys, uint32_t* __restrict__ point_list,
                        uint32_t* __restrict__ counters, SlabSource src, uint32_t* host_flags) {
     __shared__ uint64_t s[kSmallCap];
+    if (counters[kAbortFlag] != 0u) return;
     const uint32_t tile = blockIdx.x;
     const uint2 r = ranges[tile];
     const int n = (int)(r.y - r.x), tid = threadIdx.x;
@@ -386,6 +393,7 @@ tile_sort_large_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
     const int tid = threadIdx.x;
+    if (counters[kAbortFlag] != 0u) return;
     const uint32_t n_large = counters[3];
     for (uint32_t w = blockIdx.x; w < n_large; w += gridDim.x) {
         const uint32_t tile = large_tiles[w];
@@ -459,10 +467,11 @@ cudaError_t launch_duplicate(int P, const Frame& f, const Settings& s, const Geo
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const ImageState& img, cudaStream_t stream) {
+cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const ImageState& img, uint32_t capacity,
+                             cudaStream_t stream) {
     const int tiles = f.grid_x * f.grid_y;
     tile_scan_kernel<<<(tiles + kScanThreads - 1) / kScanThreads, kScanThreads, 0, stream>>>(tiles, img.tile_count, img.ranges, img.tile_cursor,
-                                                    img.large_tiles, g.counters);
+                                                    img.large_tiles, g.counters, capacity);
     return cudaGetLastError();
 }
 

@@ -116,7 +116,7 @@ __device__ __forceinline__ void stage_sh_rows(const float* __restrict__ wsrc, in
 
 }  // namespace
 
-template <bool TBC>
+template <bool TBC, bool BANDED>
 #ifndef STP_PRE_MINB
 #define STP_PRE_MINB 4  // 64 registers, 4 CTAs/SM: A/B on B200 (C5: 1.83 -> 1.47 ms)
 #endif
@@ -221,8 +221,10 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
         // exact tile count: the owner thread visits the first kSeqTiles tiles, the warp shares the rest.
         // Tile band (multi-GPU): only tiles of rows [row0,row1) are binned.  Without culling the walk is clamped to the
         // band; with culling the whole rectangle is walked, because "some tile contributes" decides visibility.
-        const int by0 = min(f.row1, max(f.row0, rc.y0)), by1 = min(f.row1, max(f.row0, rc.y1));
-        if constexpr (!TBC) {
+        // (BANDED = false: whole image, every tile of the rectangle is binned -- the single-GPU instantiation carries none
+        // of the band bookkeeping)
+        const int by0 = BANDED ? min(f.row1, max(f.row0, rc.y0)) : rc.y0, by1 = BANDED ? min(f.row1, max(f.row0, rc.y1)) : rc.y1;
+        if constexpr (!TBC && BANDED) {
             rc.y0 = by0;
             rc.y1 = by1;
         }
@@ -232,7 +234,7 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
         for (int t = 0, tx = rc.x0, ty = rc.y0; t < min(rect_tiles, kSeqTiles); ++t) {
             if (!TBC || tile_contributes(co.x, co.y, co.z, mean2D, thr, tx, ty)) {
                 ++count;
-                if (!TBC || (ty >= by0 && ty < by1)) {
+                if (!TBC || !BANDED || (ty >= by0 && ty < by1)) {
                     ++count_band;
                     atomicAdd(tile_count + ty * f.grid_x + tx, 1u);
                 }
@@ -263,7 +265,7 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
                 const int tx = x0 + t % w, ty = y0 + t / w;
                 if (!TBC || tile_contributes(A, B, C, m, th, tx, ty)) {
                     ++c;
-                    if (!TBC || (ty >= sy0 && ty < sy1)) {
+                    if (!TBC || !BANDED || (ty >= sy0 && ty < sy1)) {
                         ++cb;
                         atomicAdd(tile_count + ty * f.grid_x + tx, 1u);
                     }
@@ -273,8 +275,9 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     c += __shfl_xor_sync(0xffffffffu, c, o);
-                    cb += __shfl_xor_sync(0xffffffffu, cb, o);
+                    if constexpr (BANDED) cb += __shfl_xor_sync(0xffffffffu, cb, o);
                 }
+                if constexpr (!BANDED) cb = c;
                 if (lane == src) {
                     count += c;
                     count_band += cb;
@@ -371,13 +374,18 @@ cudaError_t launch_preprocess(const PreprocessArgs& a, const Frame& f, const Geo
     e = cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * (size_t)f.grid_x * f.grid_y, stream);
     if (e != cudaSuccess) return e;
     const size_t smem = (a.colors_precomp == nullptr && a.M > 0) ? sizeof(float) * 8 * 32 * (a.M * 3 + 1) : 0;
+    const bool banded = f.row0 > 0 || f.row1 < f.grid_y;
+#define STP_PRE(TBC_, BANDED_)                                                                                          \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(preprocess_kernel<TBC_, BANDED_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        preprocess_kernel<TBC_, BANDED_><<<blocks, kPreprocessThreads, smem, stream>>>(a, f, g, tile_count);            \
+    } while (0)
     if (tbc) {
-        cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        preprocess_kernel<true><<<blocks, kPreprocessThreads, smem, stream>>>(a, f, g, tile_count);
+        if (banded) STP_PRE(true, true); else STP_PRE(true, false);
     } else {
-        cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        preprocess_kernel<false><<<blocks, kPreprocessThreads, smem, stream>>>(a, f, g, tile_count);
+        if (banded) STP_PRE(false, true); else STP_PRE(false, false);
     }
+#undef STP_PRE
     return cudaGetLastError();
 }
 

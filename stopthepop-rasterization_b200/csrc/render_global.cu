@@ -68,6 +68,7 @@ render_global_fwd_kernel(Frame f, RenderArgs a) {
     __shared__ uint32_t s_mask[kBlock];
     __shared__ uint32_t s_id[kBlock];  // only used when the blend log is written
 
+    if (a.abort_flag != nullptr && *a.abort_flag != 0u) return;  // asynchronous forward: binning arena too small (api.cu)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
     const uint32_t px = tile_x * kTile + (warp & 1) * 8 + (lane & 7), py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);

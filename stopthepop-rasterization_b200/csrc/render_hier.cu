@@ -141,6 +141,8 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         // with a blend log the replay kernel has already handled every pixel whose log is complete: this kernel only
         // re-sorts tiles that contain a pixel with more blends than the log holds, and only for those pixels
         if (ab.blend_rec != nullptr && ab.tile_flags[tile_lin] == 0u) return;
+    } else {
+        if (a.abort_flag != nullptr && *a.abort_flag != 0u) return;  // asynchronous forward: binning arena too small
     }
 
     const uint2* __restrict__ ranges = BWD ? ab.ranges : a.ranges;

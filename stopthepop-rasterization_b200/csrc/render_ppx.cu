@@ -42,6 +42,9 @@ render_kbuffer_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     __shared__ float2 s_xy[kBlock];
     __shared__ float4 s_co[kBlock];
 
+    if constexpr (!BWD) {
+        if (a.abort_flag != nullptr && *a.abort_flag != 0u) return;  // asynchronous forward: binning arena too small
+    }
     const int tid = threadIdx.x;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
     const uint32_t px = tile_x * 16 + (tid & 15), py = tile_y * 16 + (tid >> 4);
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(kFastThreads, 1)
 render_full_fast_kernel(Frame f, RenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem_full[];
     FullFastShared& sh = *reinterpret_cast<FullFastShared*>(smem_full);
+    if (a.abort_flag != nullptr && *a.abort_flag != 0u) return;  // asynchronous forward: binning arena too small
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
     const size_t plane = (size_t)f.W * f.H;
@@ -511,6 +515,7 @@ render_full_fast_kernel(Frame f, RenderArgs a) {
 // ---- exact emulation of the reference's sliding window: long lists, and the pixels the fast path gave up on -------------
 __global__ void __launch_bounds__(kBlock)
 render_full_kernel(Frame f, RenderArgs a) {
+    if (a.abort_flag != nullptr && *a.abort_flag != 0u) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + f.row0;
     const size_t plane = (size_t)f.W * f.H;

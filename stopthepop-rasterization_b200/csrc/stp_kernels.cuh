@@ -35,6 +35,7 @@ struct RenderArgs {
     uint32_t* blend_count;
     uint32_t* tile_flags;
     uint32_t* log_overflow;  // counter: pixels whose log overflowed in a mode without list-driven backward (PPX_FULL)
+    const uint32_t* abort_flag;  // non-zero: the binning arena of this (asynchronous) frame was too small -- render nothing
     int rec_cap;
 };
 
@@ -134,7 +135,8 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* vm, ui
 
 // binning.cu
 int sort_kernel_launches();  // own kernels per tile sort
-cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const ImageState& img, cudaStream_t stream);
+cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const ImageState& img, uint32_t capacity,
+                             cudaStream_t stream);
 cudaError_t launch_duplicate(int P, const Frame& f, const Settings& s, const GeometryState& g, const int* radii,
                              const ImageState& img, const BinningState& b, size_t cap, cudaStream_t stream);
 cudaError_t launch_tile_sort(const Frame& f, const GeometryState& g, const ImageState& img, const BinningState& b,

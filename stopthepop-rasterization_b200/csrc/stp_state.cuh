@@ -13,6 +13,7 @@
 namespace stp {
 
 constexpr size_t kArenaAlign = 256;
+constexpr int kAbortFlag = 8;  // GeometryState::counters slot: the frame's instances do not fit the binning arena
 constexpr int kPreprocessThreads = 256;
 
 template <typename T>
@@ -36,7 +37,8 @@ struct GeometryState {
     uint32_t* tiles_touched;
     uint32_t* counters;  // [1] R (total instances), [2] error flags, [3] number of tiles on the large-tile sort list,
                          // [4] pixels whose blend log overflowed in PPX_FULL mode, [5..7] depth visualisation: overflow
-                         // count, min and max of the accumulated depth (order-preserving integer images)
+                         // count, min and max of the accumulated depth (order-preserving integer images),
+                         // [kAbortFlag] set by the tile scan of an asynchronous forward whose binning arena is too small
 
     static GeometryState from_chunk(char*& chunk, size_t P, bool inv) {
         GeometryState g;

@@ -68,6 +68,10 @@ _lib.stp_binning_capacity.argtypes = [ctypes.c_size_t, ctypes.POINTER(StpSetting
 _lib.stp_image_bytes.restype = ctypes.c_size_t
 _lib.stp_image_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
 _lib.stp_requires_cov3D_inv.argtypes = [ctypes.POINTER(StpSettings)]
+_lib.stp_note_num_rendered.restype = None
+_lib.stp_note_num_rendered.argtypes = [ctypes.c_int]
+_lib.stp_set_num_rendered_hint.restype = None
+_lib.stp_set_num_rendered_hint.argtypes = [ctypes.c_int]
 _lib.stp_view_geometry.argtypes = [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(StpGeometryView)]
 _lib.stp_view_binning.argtypes = [_P, ctypes.c_int, ctypes.POINTER(StpBinningView)]
 _lib.stp_view_image.argtypes = [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(StpImageView)]
@@ -85,7 +89,7 @@ _lib.stp_forward.argtypes = [
     ctypes.POINTER(StpSettings), ctypes.POINTER(StpTileBand),
     _P, _P, _P, _P, _P, ctypes.c_float, _P, _P,  # means3D shs colors opac scales mod rot cov3D
     _P, _P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_int,  # view proj inv campos tanx tany prefiltered
-    _P, _P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_int)]  # out_color radii debug stream num_rendered
+    _P, _P, ctypes.c_int, _P, _P]  # out_color radii debug stream num_rendered (host int* / pinned int[2])
 _lib.stp_backward.restype = ctypes.c_int
 _lib.stp_backward.argtypes = [
     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,  # P D M binning_bytes
@@ -192,12 +196,81 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+STP_FORWARD_ASYNC = 4  # debug bit, include/stp_rasterizer.h
+# forward passes of training steps do not wait for num_rendered (see rasterize_gaussians(async_forward=...))
+ASYNC_FORWARD_DEFAULT = os.environ.get("STP_ASYNC_FORWARD", "0") == "1"
+_pinned_pool = []
+
+
+class NumRendered:
+    """num_rendered of an ASYNCHRONOUS forward pass: the library did not wait for it (no host<->device synchronisation
+    inside the forward call); it arrives in pinned host memory and is resolved on first use -- int(), ==, formatting,
+    or the backward pass.  If the frame turned out not to fit the binning arena that had been sized from earlier frames
+    (the image is all zeros then), resolving re-runs the forward pass synchronously into the SAME output tensors and
+    replaces the three arenas (`buffers`)."""
+    __slots__ = ("_value", "_pinned", "_capacity", "_rerun", "_device", "buffers", "retried")
+
+    def __init__(self, pinned, capacity, rerun, device):
+        self._value, self._pinned, self._capacity, self._rerun, self._device = None, pinned, capacity, rerun, device
+        self.buffers, self.retried = None, False
+
+    def resolve(self):
+        if self._value is None:
+            p = self._pinned
+            spins = 0
+            while int(p[0]) < 0 or int(p[1]) < 0:  # the asynchronous copy overwrites the -1 sentinels
+                spins += 1
+                if spins > 64:
+                    torch.cuda.synchronize(self._device)
+            R, flags = int(p[0]), int(p[1])
+            self._pinned = None
+            _pinned_pool.append(p)
+            if flags & 1:  # the reference traps (auxiliary.h:226-233)
+                raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
+            with torch.cuda.device(self._device):
+                _lib.stp_note_num_rendered(R)
+            if R > self._capacity:
+                out = self._rerun()
+                R, self.buffers, self.retried = int(out[0]), tuple(out[3:6]), True
+            self._rerun = None
+            self._value = R
+        return self._value
+
+    def __int__(self):
+        return self.resolve()
+
+    __index__ = __int__
+
+    def __eq__(self, other):
+        return self.resolve() == int(other)
+
+    def __hash__(self):
+        return hash(self.resolve())
+
+    def __repr__(self):
+        return str(self.resolve())
+
+    def __format__(self, spec):
+        return format(self.resolve(), spec)
+
+    def __del__(self):
+        if self._pinned is not None and self._value is None:
+            try:  # never looked at: the slot may only be reused once the copy has landed
+                torch.cuda.synchronize(self._device)
+                _pinned_pool.append(self._pinned)
+            except Exception:
+                pass
+
+
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
                         degree, campos, prefiltered, settings_dict, render_depth, debug, tile_band=None,
-                        record_blends=True):
+                        record_blends=True, async_forward=None, _into=None):
     """record_blends (GLOBAL / HIER modes): keep the per-pixel blend log that lets the backward pass replay the blends
-    instead of sweeping the tile lists again / repeating the hierarchical re-sort; pass False for inference-only calls (GaussianRasterizer does, when no input requires a gradient)."""
+    instead of sweeping the tile lists again / repeating the hierarchical re-sort; pass False for inference-only calls (GaussianRasterizer does, when no input requires a gradient).
+    async_forward (default: environment STP_ASYNC_FORWARD=1): do not wait for num_rendered inside the call -- the first
+    element of the result is then a NumRendered that resolves itself on first use (and re-runs the frame in the rare
+    case that it outgrew the binning arena sized from earlier frames; until then the image of such a frame is black)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:68-71
     device = means3D.device
@@ -210,10 +283,18 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         e8 = torch.empty(0, dtype=torch.uint8, device=device)
         return (0, torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device),
                 torch.zeros((0,), dtype=torch.int32, device=device), e8, e8.clone(), e8.clone())
+    if async_forward is None:
+        async_forward = ASYNC_FORWARD_DEFAULT
+    async_forward = bool(async_forward) and not render_depth and not (int(debug) & 1) and _into is None
     # every pixel of the image (of the band, with tile_band) and every radius is written by the kernels
-    alloc = torch.zeros if tile_band is not None else torch.empty
-    out_color = alloc((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
-    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    if _into is not None:
+        out_color, radii = _into
+        if tile_band is not None:
+            out_color.zero_()
+    else:
+        alloc = torch.zeros if tile_band is not None else torch.empty
+        out_color = alloc((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+        radii = torch.empty((P,), dtype=torch.int32, device=device)
     geom, binning, img = _Arena(device), _Arena(device), _Arena(device)
     means3D = _f32(means3D, device)
     keep = [_f32(t, device) for t in (background, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix,
@@ -221,7 +302,13 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     background, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, sh, campos = keep
     M = sh.size(1) if sh is not None and sh.size(0) != 0 else 0
     band = ctypes.byref(StpTileBand(int(tile_band[0]), int(tile_band[1]))) if tile_band is not None else None
-    n = ctypes.c_int(0)
+    if async_forward:
+        pinned = _pinned_pool.pop() if _pinned_pool else torch.empty(2, dtype=torch.int32).pin_memory()
+        pinned.fill_(-1)
+        n_ptr = ctypes.c_void_p(pinned.data_ptr())
+    else:
+        n = ctypes.c_int(0)
+        n_ptr = ctypes.cast(ctypes.byref(n), ctypes.c_void_p)
     try:
         with torch.cuda.device(device):
             rc = _lib.stp_forward(_ALLOC_CB, geom.key, _ALLOC_CB, binning.key, _ALLOC_CB, img.key, P, int(degree), M,
@@ -229,11 +316,14 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                                   _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
                                   _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(inv_viewprojmatrix),
                                   _ptr(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
-                                  out_color.data_ptr(), radii.data_ptr(), int(debug), _stream(device), ctypes.byref(n))
+                                  out_color.data_ptr(), radii.data_ptr(),
+                                  int(debug) | (STP_FORWARD_ASYNC if async_forward else 0), _stream(device), n_ptr)
     finally:
         gt, bt, it = geom.take(), binning.take(), img.take()
     if rc != 0:
         msg = _err()
+        if async_forward:
+            _pinned_pool.append(pinned)
         if (st.blend_record_cap > 0 and st.sort_mode != 1 and not render_depth and
                 "image arena allocation failed" in msg):
             # not enough memory for the blend log: it is an optimisation (except for PPX_FULL), render without it
@@ -241,9 +331,28 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             return rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                                        cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy,
                                        image_height, image_width, sh, degree, campos, prefiltered, settings_dict,
-                                       render_depth, debug, tile_band=tile_band, record_blends=False)
+                                       render_depth, debug, tile_band=tile_band, record_blends=False,
+                                       async_forward=async_forward, _into=_into)
         raise RuntimeError(msg)
-    return n.value, out_color, radii, gt, bt, it
+    if not async_forward:
+        return n.value, out_color, radii, gt, bt, it
+    capacity = _lib.stp_binning_capacity(bt.numel(), ctypes.byref(st))
+
+    def rerun():
+        import warnings
+        warnings.warn("diff_gaussian_rasterization: an asynchronous forward pass outgrew its binning arena "
+                      f"(capacity {capacity}); the frame is rendered again synchronously")
+        return rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                                   cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy,
+                                   image_height, image_width, sh, degree, campos, prefiltered, settings_dict,
+                                   render_depth, debug, tile_band=tile_band, record_blends=record_blends,
+                                   async_forward=False, _into=(out_color, radii))
+    # on a device without history the library falls back to the synchronous path: it then wrote R itself and marked [1]
+    if int(pinned[1]) == -2:
+        R = int(pinned[0])
+        _pinned_pool.append(pinned)
+        return R, out_color, radii, gt, bt, it
+    return NumRendered(pinned, capacity, rerun, device), out_color, radii, gt, bt, it
 
 
 def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, scales, rotations, scale_modifier,
@@ -259,6 +368,10 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
     arrays remain exposed.
     Tile bands (tile_band given): the packed screen-space accumulator (48 B/Gaussian) is all-reduced between the two
     backward stages instead (_backward_band_exchange); all eight returned gradients are then the full-frame ones."""
+    if isinstance(R, NumRendered):  # asynchronous forward: look at num_rendered now; a frame that did not fit was re-run
+        R.resolve()
+        if R.buffers is not None:
+            geomBuffer, binningBuffer, imageBuffer = R.buffers
     device = means3D.device
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)  # rasterize_points.cu:169-170

@@ -50,6 +50,7 @@ def rasterize_gaussians(
     raster_settings,
     tile_band=None,
     sync_group=None,
+    async_forward=None,
 ):
     # The blend log (2 KB per pixel) only pays off when a backward pass will follow.  Decided HERE, not inside
     # Function.forward: there grad mode is always off and ctx.needs_input_grad reflects requires_grad even under
@@ -70,6 +71,7 @@ def rasterize_gaussians(
         tile_band,
         sync_group,
         record_blends,
+        async_forward,
     )
 
 
@@ -78,9 +80,10 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, tile_band=None, sync_group=None, record_blends=None):
+                raster_settings, tile_band=None, sync_group=None, record_blends=None, async_forward=None):
         # tile_band (ours only, multi-GPU tile sharding): (row0, row1) of 16-pixel tile rows this rank renders
         # sync_group (ours only): process group over which backward sums the parameter gradients (overlapped exchange)
+        # async_forward (ours only): do not wait for num_rendered inside the forward call (_C.NumRendered)
         rs = raster_settings
         if record_blends is None:  # direct .apply callers: the wrapper above knows better (grad mode)
             record_blends = any(ctx.needs_input_grad)
@@ -95,14 +98,14 @@ class _RasterizeGaussians(torch.autograd.Function):
             cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
             try:
                 num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(
-                    *args, record_blends=record_blends, tile_band=tile_band)
+                    *args, record_blends=record_blends, tile_band=tile_band, async_forward=async_forward)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
             num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(
-                *args, record_blends=record_blends, tile_band=tile_band)
+                *args, record_blends=record_blends, tile_band=tile_band, async_forward=async_forward)
 
         ctx.raster_settings = rs
         ctx.tile_band = tile_band
@@ -119,6 +122,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         (colors_precomp, means3D, opacities, scales, rotations, cov3Ds_precomp, radii, sh, color, geomBuffer,
          binningBuffer, imgBuffer) = ctx.saved_tensors
+        # (an asynchronous forward pass hands over a lazily resolved num_rendered; the native call below resolves it and,
+        # should the frame have outgrown its binning arena, uses the buffers of the re-run instead of the saved ones)
         args = (rs.bg, means3D, radii, opacities, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 rs.viewmatrix, rs.projmatrix, rs.inv_viewprojmatrix, rs.tanfovx, rs.tanfovy, color, grad_out_color, sh,
                 rs.sh_degree, rs.campos, geomBuffer, num_rendered, binningBuffer, imgBuffer, ctx.settings_dict,
@@ -144,6 +149,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_scales,
             grad_rotations,
             grad_cov3Ds_precomp,
+            None,
             None,
             None,
             None,
@@ -289,7 +295,7 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings, tile_band=None, sync_group=None):
+    def __init__(self, raster_settings, tile_band=None, sync_group=None, async_forward=None):
         """tile_band (ours only): (row0, row1) band of 16-pixel tile rows rendered / differentiated by this rank when
         one view is sharded across GPUs (stp_sharding.py); None = the whole image, as in the reference.
         sync_group (ours only): torch.distributed process group; backward returns parameter gradients already summed
@@ -298,6 +304,7 @@ class GaussianRasterizer(nn.Module):
         self.raster_settings = raster_settings
         self.tile_band = tile_band
         self.sync_group = sync_group
+        self.async_forward = async_forward  # None: environment STP_ASYNC_FORWARD (default off); see _C.NumRendered
 
     def markVisible(self, positions):
         # Mark visible points (based on frustum culling for camera) with a boolean
@@ -330,4 +337,4 @@ class GaussianRasterizer(nn.Module):
 
         # Invoke the CUDA rasterization routine
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                   raster_settings, self.tile_band, self.sync_group)
+                                   raster_settings, self.tile_band, self.sync_group, self.async_forward)

@@ -337,3 +337,55 @@ def test_two_devices_in_one_process():
         results.append(per_mode)
     for a, b in zip(*results):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+def test_async_forward_matches_sync_and_recovers_from_overflow(mode):
+    """asynchronous forward (no host<->device synchronisation inside the call): (1) with a history of
+    num_rendered on the device the result equals the synchronous one and num_rendered resolves lazily; (2) with a far too
+    small hint the frame does not fit the binning arena: the kernels abort (black image), resolving num_rendered -- here
+    through the backward call -- re-runs the frame into the same tensors, and image / gradients equal the synchronous
+    ones."""
+    import warnings
+    import stp_scenes as S
+    from diff_gaussian_rasterization import _C
+    dev = _dev()
+    W, H, P = 256, 160, 20000
+    sc, cam = S.make_scene(P, W, H, 77, sigma_scale=0.5)
+    sc, cam = S.to_device(sc, dev), S.to_device(cam, dev)
+    d = S.default_settings_dict(sort_mode=mode)
+    e = torch.empty(0, device=dev)
+    dL = S.make_upstream_grad(W, H, 78).to(dev)
+
+    def fwd(async_forward):
+        return _C.rasterize_gaussians(cam.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e, cam.viewmatrix,
+                                      cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx, cam.tanfovy, H, W, sc.shs, 3,
+                                      cam.campos, False, d, False, False, async_forward=async_forward)
+    base = fwd(False)
+    g_base = ours_backward(sc, cam, d, base, dL)
+    assert isinstance(base[0], int) and base[0] > 1000
+    # (1) history present (the synchronous call above recorded R)
+    out = fwd(True)
+    assert isinstance(out[0], _C.NumRendered)
+    assert torch.equal(out[1], base[1]) and torch.equal(out[2], base[2])
+    assert int(out[0]) == base[0] and not out[0].retried
+    for a, b in zip(ours_backward(sc, cam, d, out, dL), g_base):
+        assert (a - b).abs().max().item() <= TOL * max(b.abs().max().item(), 1e-30)
+    # (2) overflow: pretend the device has only ever seen 64 instances
+    with torch.cuda.device(dev):
+        _C._lib.stp_set_num_rendered_hint(64)
+    out = fwd(True)
+    assert isinstance(out[0], _C.NumRendered)
+    torch.cuda.synchronize()
+    assert out[1].abs().max().item() == 0.0  # aborted frame: black, not garbage
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        grads = ours_backward(sc, cam, d, out, dL)  # resolves num_rendered -> re-run -> backward on the new buffers
+    assert out[0].retried and any("outgrew" in str(x.message) for x in w)
+    assert int(out[0]) == base[0]
+    assert torch.equal(out[1], base[1]) and torch.equal(out[2], base[2])
+    for a, b in zip(grads, g_base):
+        assert (a - b).abs().max().item() <= TOL * max(b.abs().max().item(), 1e-30)
+    # the hint has been raised by the resolved R: the next asynchronous frame fits
+    out = fwd(True)
+    assert int(out[0]) == base[0] and not out[0].retried and torch.equal(out[1], base[1])
