@@ -572,9 +572,10 @@ def main():
     ap.add_argument("--bands", default="balanced", choices=["balanced", "equal"],
                     help="tile-row bands of equal instance count (from a warm-up frame) or of equal height")
     ap.add_argument("--points", type=int, default=0, help="override the number of Gaussians of the workload's scene")
-    ap.add_argument("--sync-forward", dest="async_forward", action="store_false",
-                    help="ours: wait for num_rendered inside every forward call (the reference's behaviour) instead of the "
-                         "asynchronous forward (GaussianRasterizer(async_forward=True): no host<->device synchronisation)")
+    ap.add_argument("--async-forward", dest="async_forward", action="store_true",
+                    help="ours: GaussianRasterizer(async_forward=True) -- no host<->device synchronisation inside the forward "
+                         "call, num_rendered resolved lazily (measured on B200: no difference, the synchronous call's "
+                         "bubble is already hidden by the speculative arena request; profiles/r02_async_forward.txt)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations")
     ap.add_argument("--trace-steps", action="store_true", help="diagnostics: per-step times of every timed region")

@@ -217,12 +217,19 @@ class NumRendered:
     def resolve(self):
         if self._value is None:
             p = self._pinned
-            spins = 0
-            while int(p[0]) < 0 or int(p[1]) < 0:  # the asynchronous copy overwrites the -1 sentinels
-                spins += 1
-                if spins > 64:
-                    torch.cuda.synchronize(self._device)
-            R, flags = int(p[0]), int(p[1])
+            # busy-wait on the pinned words (the asynchronous copy overwrites the -1 sentinels): the copy sits right
+            # behind the preprocess kernel of the frame, so this returns long before the frame has finished rendering --
+            # a stream / device synchronisation here would drain the whole queue and open a bubble before the backward pass
+            raw = (ctypes.c_int32 * 2).from_address(p.data_ptr())
+            if raw[0] < 0 or raw[1] < 0:
+                import time
+                t0 = time.perf_counter()
+                while raw[0] < 0 or raw[1] < 0:
+                    if time.perf_counter() - t0 > 30.0:
+                        torch.cuda.synchronize(self._device)  # surfaces a launch failure, if that is what happened
+                        if raw[0] < 0 or raw[1] < 0:
+                            raise RuntimeError("asynchronous forward: num_rendered never arrived")
+            R, flags = int(raw[0]), int(raw[1])
             self._pinned = None
             _pinned_pool.append(p)
             if flags & 1:  # the reference traps (auxiliary.h:226-233)
