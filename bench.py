@@ -336,10 +336,22 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
         band_box["band"] = bands[rank]
         del out0
 
+    gather_stream = torch.cuda.Stream(device=dev) if bands is not None else None
+
+    def gather_bands(img):
+        """the ONE forward exchange of tile sharding, on a side stream: it overlaps the render-backward stage (nothing
+        on this rank's backward path needs the other ranks' bands); the step waits for it at its end"""
+        main = torch.cuda.current_stream(dev)
+        gather_stream.wait_stream(main)
+        with torch.cuda.stream(gather_stream):
+            full = SH.gather_image_bands(img, bands)
+        img.record_stream(gather_stream)
+        return full
+
     def step_resident():
         out = fwd(cam)
         if bands is not None:
-            state["image"] = SH.gather_image_bands(out[1], bands)  # the ONE forward exchange of tile sharding
+            state["image"] = gather_bands(out[1])
         if full_sort_ref:
             state["out"] = out
             return
@@ -347,6 +359,8 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
         if use_dist and a.impl != "ours":
             for t in (slab[3], slab[5], slab[2], slab[6], slab[7]):
                 dist.all_reduce(t)
+        if bands is not None:
+            torch.cuda.current_stream(dev).wait_stream(gather_stream)
         state["out"], state["grads"] = out, grads
 
     # ---- e2e: public API, per-step host inputs -------------------------------------------------------------
@@ -354,8 +368,16 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
     h_cam = [pin(t) for t in (cam_c.viewmatrix, cam_c.projmatrix, cam_c.inv_viewprojmatrix, cam_c.campos, cam_c.bg)]
     h_dL = pin(dL_c)
     h_img = torch.empty(3, H, W, dtype=torch.float32).pin_memory()
-    h2d = sum(t.numel() * 4 for t in h_cam) + h_dL.numel() * 4
-    d2h = h_img.numel() * 4
+    # tile bands: a rank only consumes the upstream gradient of ITS band and only produces its band of the image, so
+    # that is what it moves over PCIe (pixel rows [r0, r1)); the byte counts are totals over all ranks
+    if bands is not None:
+        prow = (min(bands[rank][0] * 16, H), min(bands[rank][1] * 16, H))
+        h2d = sum(t.numel() * 4 for t in h_cam) * world + h_dL.numel() * 4
+        d2h = h_img.numel() * 4
+    else:
+        prow = (0, H)
+        h2d = (sum(t.numel() * 4 for t in h_cam) + h_dL.numel() * 4) * (eff_world if per_rank_view else 1)
+        d2h = h_img.numel() * 4 * (eff_world if per_rank_view else 1)
     leaves = [t.clone().requires_grad_(True) for t in (sc.means3D, sc.opacities, sc.shs, sc.scales, sc.rotations)]
     means2D = torch.zeros_like(sc.means3D, requires_grad=True)
 
@@ -371,7 +393,7 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
         vm, pm, iv, cp, bg = [t.to(dev, non_blocking=True) for t in h_cam]
         copy_stream.wait_stream(main)  # g_dev / h_img of the previous step are no longer in use
         with torch.cuda.stream(copy_stream):
-            g_dev.copy_(h_dL, non_blocking=True)
+            g_dev[:, prow[0]:prow[1]].copy_(h_dL[:, prow[0]:prow[1]], non_blocking=True)
             ev_g.record(copy_stream)
         for t in leaves + [means2D]:
             t.grad = None
@@ -384,16 +406,16 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
                                               async_forward=a.async_forward)(
                 m3, means2D, op, shs=sh, scales=scl, rotations=rot)
             if bands is not None:
-                color_full = SH.gather_image_bands(color.detach(), bands)
+                color_full = gather_bands(color.detach())
         else:
             c = cam._replace(viewmatrix=vm, projmatrix=pm, inv_viewprojmatrix=iv, campos=cp, bg=bg)
             out = ref.forward(sc, c, settings)
             color = out[1]
-        img_out = color_full if color_full is not None else color.detach()
+        img_out = color.detach()  # (bands: this rank's rows; the gathered frame stays on the GPUs)
         ev_f.record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_f)
-            h_img.copy_(img_out, non_blocking=True)
+            h_img[:, prow[0]:prow[1]].copy_(img_out[:, prow[0]:prow[1]], non_blocking=True)
         img_out.record_stream(copy_stream)
         main.wait_event(ev_g)
         if full_sort_ref:
@@ -407,6 +429,9 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
                 for t in (grads[3], grads[5], grads[2], grads[6], grads[7]):
                     dist.all_reduce(t)
         main.wait_stream(copy_stream)
+        if bands is not None:
+            main.wait_stream(gather_stream)
+            state["image_e2e"] = color_full
 
     # full-upload variant: every Gaussian parameter host->device, every parameter gradient device->host
     h_params = [pin(t) for t in (sc_c.means3D, sc_c.opacities, sc_c.shs, sc_c.scales, sc_c.rotations)] if full else []

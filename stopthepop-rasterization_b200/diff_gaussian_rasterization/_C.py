@@ -418,7 +418,7 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
             if sync_group is None:
                 rc = _lib.stp_backward(*args)
             elif tile_band is not None:
-                rc = _backward_band_exchange(args, P, grad_accum, sync_group)
+                rc = _backward_band_exchange(args, P, grad_accum, sync_group, device, int(sync_chunks))
             else:
                 rc = _backward_overlapped(args, P, M, dL_dsh, flat[offs[1]:offs[5]], sync_group,
                                           int(sync_chunks), device)
@@ -475,18 +475,39 @@ def _backward_overlapped(args, P, M, dL_dsh, small, group, chunks, device):
     return 0
 
 
-def _backward_band_exchange(args, P, grad_accum, group):
+def _backward_band_exchange(args, P, grad_accum, group, device, chunks=4):
     """tile-band sharding (one view, bands of tile rows per rank): the per-Gaussian backward is linear in the packed
     screen-space gradients, and every rank holds the geometry state of every visible Gaussian (visibility does not
     depend on the band, preprocess.cu), so the ONE exchange is an all-reduce of the 48 B/Gaussian accumulator between
     the render-backward and the preprocess-backward stage -- 5x less than the 236 B/Gaussian of parameter gradients
-     -- after which every rank finishes the same preprocess-backward and holds the full gradients."""
+     -- after which every rank finishes the same preprocess-backward and holds the full gradients.
+    The exchange is pipelined with that stage: the accumulator is reduced in `chunks` ranges of Gaussians on a side
+    stream, and the preprocess-backward of a range starts as soon as its sum has arrived."""
     import torch.distributed as dist
     rc = _lib.stp_backward_render(*args)
     if rc != 0:
         return rc
-    dist.all_reduce(grad_accum, group=group)
-    return _lib.stp_backward_preprocess(*args, 0, P)
+    main = torch.cuda.current_stream(device)
+    comm = _comm_streams.get(device)
+    if comm is None:
+        comm = _comm_streams[device] = torch.cuda.Stream(device=device)
+    step = max(256, ((P + max(chunks, 1) - 1) // max(chunks, 1) + 255) // 256 * 256)
+    ranges, events = [], []
+    comm.wait_stream(main)
+    with torch.cuda.stream(comm):
+        for first in range(0, P, step):
+            count = min(step, P - first)
+            dist.all_reduce(grad_accum[first * 12:(first + count) * 12], group=group)
+            ev = torch.cuda.Event()
+            ev.record(comm)
+            ranges.append((first, count))
+            events.append(ev)
+    for (first, count), ev in zip(ranges, events):
+        main.wait_event(ev)
+        rc = _lib.stp_backward_preprocess(*args, first, count)
+        if rc != 0:
+            return rc
+    return 0
 
 
 def blend_record_cap_of(imageBuffer, W, H):

@@ -97,12 +97,3 @@ def gather_image_bands(local_img: torch.Tensor, bands: Sequence[Tuple[int, int]]
     for r, (s, e) in enumerate(px):
         full[:, s:e] = recv[r, :, :e - s]
     return full
-
-
-def rasterize_band_sharded(C_mod, args_fwd: dict, bands: Sequence[Tuple[int, int]], group=None):
-    """forward of one view sharded by tile-row bands.  `C_mod` is diff_gaussian_rasterization._C, `args_fwd` the
-    keyword-free positional argument list of `_C.rasterize_gaussians` as a dict {'args': tuple}.  Returns
-    (full image, local forward outputs)."""
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    out = C_mod.rasterize_gaussians(*args_fwd["args"], tile_band=bands[rank])
-    return gather_image_bands(out[1], bands, group), out
