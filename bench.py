@@ -385,6 +385,10 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
     # under the forward pass, the image download under the backward pass; the step ends when both streams are done
     copy_stream = torch.cuda.Stream(device=dev)
     g_dev = torch.empty_like(dL)
+    if bands is not None:  # strided host<->device copies would be staged through pageable memory by torch
+        h_dL_band = h_dL[:, prow[0]:prow[1]].contiguous().pin_memory()
+        h_img_band = torch.empty(3, prow[1] - prow[0], W, dtype=torch.float32).pin_memory()
+        g_band = torch.empty(3, prow[1] - prow[0], W, dtype=torch.float32, device=dev)
     ev_g, ev_f = torch.cuda.Event(), torch.cuda.Event()
     ext_settings = ExtendedSettings.from_dict(settings) if a.impl == "ours" else None
 
@@ -393,7 +397,11 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
         vm, pm, iv, cp, bg = [t.to(dev, non_blocking=True) for t in h_cam]
         copy_stream.wait_stream(main)  # g_dev / h_img of the previous step are no longer in use
         with torch.cuda.stream(copy_stream):
-            g_dev[:, prow[0]:prow[1]].copy_(h_dL[:, prow[0]:prow[1]], non_blocking=True)
+            if bands is None:
+                g_dev.copy_(h_dL, non_blocking=True)
+            else:  # contiguous pinned band -> contiguous device staging -> the band's rows of the gradient image
+                g_band.copy_(h_dL_band, non_blocking=True)
+                g_dev[:, prow[0]:prow[1]].copy_(g_band)
             ev_g.record(copy_stream)
         for t in leaves + [means2D]:
             t.grad = None
@@ -415,7 +423,10 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
         ev_f.record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_f)
-            h_img[:, prow[0]:prow[1]].copy_(img_out[:, prow[0]:prow[1]], non_blocking=True)
+            if bands is None:
+                h_img.copy_(img_out, non_blocking=True)
+            else:
+                h_img_band.copy_(img_out[:, prow[0]:prow[1]].contiguous(), non_blocking=True)
         img_out.record_stream(copy_stream)
         main.wait_event(ev_g)
         if full_sort_ref:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define STP_ABI_VERSION 5
+#define STP_ABI_VERSION 6
 
 /* replaces: enum SortMode / GlobalSortOrder, rasterizer.h:27-41 */
 enum { STP_SORT_GLOBAL = 0, STP_SORT_PPX_FULL = 1, STP_SORT_PPX_KBUFFER = 2, STP_SORT_HIER = 3 };
@@ -62,12 +62,21 @@ typedef struct StpSettings {
      * backward pass (8 B each, in the image arena; stp_image_bytes).  0 = none: backward repeats the re-sort.
      * Must have the same value in stp_forward and the matching stp_backward. */
     int32_t blend_record_cap;
-    /* replaces DebugVisualizationData::type (rasterizer_debug.h:11-20) as far as the Python API can reach it:
-     * 0 = disabled, STP_DEBUG_DEPTH = what render_depth=True selects (rasterize_points.cu:104-107): out_color becomes
-     * the Turbo-coloured, min/max-normalised accumulated depth.  Forward only; needs blend_record_cap > 0. */
+    /* replaces DebugVisualizationData (rasterizer_debug.h:11-56): 0 = disabled, else one of STP_DEBUG_*: out_color becomes
+     * the colour-mapped (Turbo for Depth, Magma for the others), min/max-normalised visualisation.  STP_DEBUG_DEPTH is what
+     * render_depth=True of the Python API selects (rasterize_points.cu:104-107).  Forward only; all types except
+     * COUNT_PER_TILE and TRANSMITTANCE need blend_record_cap > 0. */
     int32_t debug_visualization;
+    int32_t debug_normalize;  /* normalise with [debug_min, debug_max] instead of the frame's own range (minMax) */
+    float debug_min, debug_max;
+    int32_t debug_pixel_x, debug_pixel_y; /* debugPixel: its raw value is reported by stp_last_debug_stats */
 } StpSettings;
-#define STP_DEBUG_DEPTH 4 /* DebugVisualization::Depth */
+#define STP_DEBUG_SORT_ERROR_OPACITY 1  /* DebugVisualization::SortErrorOpacity      */
+#define STP_DEBUG_SORT_ERROR_DISTANCE 2 /* DebugVisualization::SortErrorDistance     */
+#define STP_DEBUG_COUNT_PER_TILE 3      /* DebugVisualization::GaussianCountPerTile  */
+#define STP_DEBUG_DEPTH 4               /* DebugVisualization::Depth                 */
+#define STP_DEBUG_COUNT_PER_PIXEL 5     /* DebugVisualization::GaussianCountPerPixel */
+#define STP_DEBUG_TRANSMITTANCE 6       /* DebugVisualization::Transmittance         */
 
 /* replaces: std::function<char*(size_t)> geometryBuffer/binningBuffer/imageBuffer,
  * rasterizer.h:195-198 (resizeFunctional, rasterize_points.cu:33-41).  Must return a device
@@ -239,6 +248,9 @@ void stp_timing_reset(void);
 /* cumulative number of hand-written kernels this thread has launched through stp_forward/stp_backward
  * (there is no library kernel on the path; memsets are not counted) -- bench.py reports the per-step difference. */
 long long stp_kernel_launches(void);
+/* statistics of the raw (pre-colormap) values of the last debug visualisation rendered on this thread -- the arguments
+ * of DebugVisualizationData::dataCallback (rasterizer_impl.cu:97): value at the debug pixel, min, max, mean, std */
+void stp_last_debug_stats(float* out5);
 
 const char* stp_last_error(void);
 int stp_abi_version(void);

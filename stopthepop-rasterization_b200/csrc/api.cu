@@ -5,7 +5,9 @@
 // Everything is enqueued on the caller's stream; the only host<->device synchronisation is the
 // read-back of num_rendered that sizes the binning arena (the reference blocks in the same place,
 // rasterizer_impl.cu:317).
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <mutex>
 #include <cstring>
@@ -20,6 +22,7 @@ using namespace stp;
 namespace {
 
 thread_local std::string g_error;
+thread_local float g_debug_stats[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // value at the debug pixel, min, max, mean, std
 thread_local long long g_launches = 0;  // hand-written kernels launched by this thread (stp_kernel_launches)
 thread_local std::vector<std::pair<const char*, float>> g_timings;
 
@@ -100,16 +103,23 @@ bool convert_settings(const StpSettings* in, Settings& s, std::string& err, bool
     s.tile_based_culling = in->tile_based_culling != 0;
     s.hier_culling = in->hierarchical_4x4_culling != 0;
     s.proper_ewa_scaling = in->proper_ewa_scaling != 0;
-    s.render_depth = !backward && in->debug_visualization == STP_DEBUG_DEPTH;
-    if (!backward && in->debug_visualization != 0 && in->debug_visualization != STP_DEBUG_DEPTH) {
-        err = "unsupported debug_visualization (only STP_DEBUG_DEPTH = render_depth is provided)";
+    s.debug_vis = backward ? 0 : in->debug_visualization;
+    s.render_depth = s.debug_vis != 0;  // out_color receives a visualisation instead of the colour image
+    if (s.debug_vis < 0 || s.debug_vis > STP_DEBUG_TRANSMITTANCE) {
+        err = "invalid debug_visualization";
         return false;
     }
-    // the k-buffer forward only writes a log for the depth visualisation (its backward re-sorts)
-    s.rec_cap = ((in->sort_mode != STP_SORT_PPX_KBUFFER || s.render_depth) && in->blend_record_cap > 0)
+    s.debug_normalize = in->debug_normalize != 0;
+    s.debug_min = in->debug_min;
+    s.debug_max = in->debug_max;
+    s.debug_px = in->debug_pixel_x;
+    s.debug_py = in->debug_pixel_y;
+    const bool vis_needs_log = s.debug_vis != 0 && s.debug_vis != STP_DEBUG_COUNT_PER_TILE && s.debug_vis != STP_DEBUG_TRANSMITTANCE;
+    // the k-buffer forward only writes a log for the visualisations (its backward re-sorts)
+    s.rec_cap = ((in->sort_mode != STP_SORT_PPX_KBUFFER || vis_needs_log) && in->blend_record_cap > 0)
                     ? in->blend_record_cap : 0;
-    if (s.render_depth && s.rec_cap == 0) {
-        err = "render_depth needs the blend log (blend_record_cap > 0)";
+    if (vis_needs_log && s.rec_cap == 0) {
+        err = "render_depth / debug visualisations need the blend log (blend_record_cap > 0)";
         return false;
     }
     if (s.sort_mode == STP_SORT_HIER) {
@@ -257,6 +267,9 @@ int stp_timing_summary(float* mean_ms, const char** names, int* counts, int max_
 
 void stp_timing_reset(void) { destroy_pending(); }
 long long stp_kernel_launches(void) { return g_launches; }
+void stp_last_debug_stats(float* out5) {
+    if (out5 != nullptr) std::memcpy(out5, g_debug_stats, sizeof(g_debug_stats));
+}
 
 int stp_requires_cov3D_inv(const StpSettings* s) {
     if (s == nullptr) return 0;
@@ -474,6 +487,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     ra.tile_flags = img.tile_flags;
     ra.log_overflow = g.counters + 4;
     ra.abort_flag = async ? g.counters + kAbortFlag : nullptr;
+    ra.full_sort_ray = false;
     ra.rec_cap = s.rec_cap;
     if (s.sort_mode == STP_SORT_GLOBAL) {
         STP_CUDA(launch_render_global_fwd(f, ra, stream), "render (GLOBAL)");
@@ -486,18 +500,44 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     }
     g_launches += (s.sort_mode == STP_SORT_PPX_FULL) ? 2 : 1;
     timer.mark("Render");
-    if (s.render_depth) {  // rasterizer_impl.cu:402-413 (applyDebugVisualization) for DebugVisualization::Depth
-        STP_CUDA(launch_depth_visualisation(f, ra, s.sort_mode, means3D, g.counters, stream), "depth visualisation");
-        g_launches += 2;
-        uint32_t overflowed = 0;
-        cudaError_t e = cudaMemcpyAsync(&overflowed, g.counters + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+    if (s.debug_vis != 0) {  // rasterizer_impl.cu:54-109, 402-413 (applyDebugVisualization)
+        ra.full_sort_ray = s.sort_mode == STP_SORT_PPX_FULL;
+        STP_CUDA(launch_debug_visualisation(f, ra, s, means3D, g.counters, stream), "debug visualisation");
+        // raw values are in out_color now: statistics for the viewer's read-out, then the colormap
+        uint32_t raw[9];  // counters[5..13]: overflow count, min, max (ordered bits), -, -, sum and sum of squares (doubles)
+        struct { uint32_t overflowed, mn, mx; double s1, s2; } h;
+        float at_pixel = 0.f;
+        cudaError_t e = cudaMemcpyAsync(raw, g.counters + 5, sizeof(raw), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess && s.debug_px > 0 && s.debug_px < width && s.debug_py > 0 && s.debug_py < height)
+            e = cudaMemcpyAsync(&at_pixel, out_color + (size_t)width * s.debug_py + s.debug_px, sizeof(float),
+                                cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) return cuda_fail(e, "depth visualisation");
-        if (overflowed != 0)
-            return fail(STP_ERR_UNSUPPORTED, "render_depth: " + std::to_string(overflowed) +
+        if (e != cudaSuccess) return cuda_fail(e, "debug visualisation");
+        h.overflowed = raw[0];
+        h.mn = raw[1];
+        h.mx = raw[2];
+        std::memcpy(&h.s1, raw + 5, sizeof(double));
+        std::memcpy(&h.s2, raw + 7, sizeof(double));
+        if (h.overflowed != 0)
+            return fail(STP_ERR_UNSUPPORTED, "render_depth: " + std::to_string(h.overflowed) +
                                                  " pixels blended more than blend_record_cap entries; raise "
                                                  "STP_BLEND_RECORD_CAP");
-        timer.mark("DepthVisualisation");
+        const double n_pix = (double)width * (double)(std::min(f.row1 * 16, height) - std::min(f.row0 * 16, height));
+        auto unorder = [](uint32_t u) {
+            const uint32_t b = u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu);
+            float v;
+            std::memcpy(&v, &b, sizeof(v));
+            return v;
+        };
+        const double mean = n_pix > 0 ? h.s1 / n_pix : 0.0, var = n_pix > 0 ? std::max(0.0, h.s2 / n_pix - mean * mean) : 0.0;
+        g_debug_stats[0] = at_pixel;
+        g_debug_stats[1] = unorder(h.mn);
+        g_debug_stats[2] = unorder(h.mx);
+        g_debug_stats[3] = (float)mean;
+        g_debug_stats[4] = (float)std::sqrt(var);
+        STP_CUDA(launch_debug_colormap(f, ra, s, g.counters, stream), "debug visualisation");
+        g_launches += 2;
+        timer.mark("DebugVisualisation");
     }
     timer.finish();
     if (debug & 1) {  // every stage has been synchronised: flags raised by this very call are visible

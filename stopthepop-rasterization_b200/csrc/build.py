@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB = os.path.join(LIB_DIR, "libstp_rasterizer.so")
 SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "render_global.cu", "render_hier.cu", "render_ppx.cu",
-           "preprocess_bwd.cu", "depth_vis.cu"]
+           "preprocess_bwd.cu", "debug_vis.cu", "rasterizer_shim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--compiler-options", "-fPIC", "-Xptxas", "-v", "-Xcudafe", "--diag_suppress=177"]
 

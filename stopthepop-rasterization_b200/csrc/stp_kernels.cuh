@@ -1,5 +1,6 @@
 // stp_kernels.cuh -- kernel argument packs and host-side launchers (one per pipeline stage).
 #pragma once
+#include "../../include/stp_rasterizer.h"
 #include "stp_math.cuh"
 #include "stp_state.cuh"
 
@@ -36,6 +37,7 @@ struct RenderArgs {
     uint32_t* tile_flags;
     uint32_t* log_overflow;  // counter: pixels whose log overflowed in a mode without list-driven backward (PPX_FULL)
     const uint32_t* abort_flag;  // non-zero: the binning arena of this (asynchronous) frame was too small -- render nothing
+    bool full_sort_ray;          // debug visualisation of PPX_FULL: depths on the ray as that mode's kernels round it
     int rec_cap;
 };
 
@@ -161,9 +163,12 @@ cudaError_t launch_render_kbuffer_bwd(const Frame& f, const Settings& s, const R
 cudaError_t launch_render_full_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream);
 cudaError_t launch_render_full_bwd(const Frame& f, const RenderBwdArgs& a, cudaStream_t stream);
 
-// depth_vis.cu: render_depth=True (DebugVisualization::Depth) from the blend log of the forward pass
-cudaError_t launch_depth_visualisation(const Frame& f, const RenderArgs& a, int sort_mode, const float* means3D,
+// debug_vis.cu: DebugVisualization types (render_depth=True = Depth) from the blend log of the forward pass: raw values
+// + min / max / moments into out_color / counters, then the colormap
+cudaError_t launch_debug_visualisation(const Frame& f, const RenderArgs& a, const Settings& s, const float* means3D,
                                        uint32_t* counters, cudaStream_t stream);
+cudaError_t launch_debug_colormap(const Frame& f, const RenderArgs& a, const Settings& s, const uint32_t* counters,
+                                  cudaStream_t stream);
 
 // preprocess_bwd.cu
 cudaError_t launch_preprocess_bwd(const PreprocessBwdArgs& a, const Frame& f, cudaStream_t stream);

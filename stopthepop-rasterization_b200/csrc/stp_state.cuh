@@ -146,7 +146,11 @@ struct Settings {
     int q_mid, q_head;
     bool rect_bounding, tight_opacity_bounding, tile_based_culling, hier_culling, proper_ewa_scaling;
     int rec_cap;  // blend records per pixel (0 = none)
-    bool render_depth;  // DebugVisualization::Depth instead of the colour image
+    bool render_depth;  // a debug visualisation instead of the colour image (render_depth=True of the Python API: Depth)
+    int debug_vis;      // STP_DEBUG_* (0 = none)
+    bool debug_normalize;
+    float debug_min, debug_max;
+    int debug_px, debug_py;
     bool per_tile_depth() const { return sort_order == 2 || sort_order == 3; }
     bool requires_inv() const { return sort_mode != 0 || per_tile_depth(); }
     bool uses_slab() const { return sort_mode != 0; }  // HIER / PPX_FULL / PPX_KBUFFER render from per-tile slabs

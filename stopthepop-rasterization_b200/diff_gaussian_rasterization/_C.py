@@ -34,7 +34,9 @@ class StpSettings(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "sort_mode", "sort_order", "queue_tile_4x4", "queue_tile_2x2", "queue_per_pixel", "rect_bounding",
         "tight_opacity_bounding", "tile_based_culling", "hierarchical_4x4_culling", "load_balancing",
-        "proper_ewa_scaling", "blend_record_cap", "debug_visualization")]
+        "proper_ewa_scaling", "blend_record_cap", "debug_visualization", "debug_normalize")] + [
+        ("debug_min", ctypes.c_float), ("debug_max", ctypes.c_float), ("debug_pixel_x", ctypes.c_int32),
+        ("debug_pixel_y", ctypes.c_int32)]
 
 
 class StpTileBand(ctypes.Structure):
@@ -105,7 +107,7 @@ _lib.stp_backward_render.argtypes = list(_lib.stp_backward.argtypes)
 _lib.stp_backward_preprocess.restype = ctypes.c_int
 _lib.stp_backward_preprocess.argtypes = list(_lib.stp_backward.argtypes) + [ctypes.c_int, ctypes.c_int]
 
-if _lib.stp_abi_version() != 5:
+if _lib.stp_abi_version() != 6:
     raise ImportError("libstp_rasterizer.so ABI version mismatch")
 
 LIBRARY_PATH = _LIB_PATH
@@ -125,20 +127,28 @@ BLEND_RECORD_CAP = int(os.environ.get("STP_BLEND_RECORD_CAP", "256"))
 BLEND_RECORD_MODES = (0, 1, 3) if os.environ.get("STP_BLEND_RECORD_GLOBAL", "0") == "1" else (1, 3)
 
 
-STP_DEBUG_DEPTH = 4  # DebugVisualization::Depth, rasterizer_debug.h:11-20
+# DebugVisualization (rasterizer_debug.h:11-20) -> STP_DEBUG_* of include/stp_rasterizer.h
+STP_DEBUG_SORT_ERROR_OPACITY, STP_DEBUG_SORT_ERROR_DISTANCE, STP_DEBUG_COUNT_PER_TILE = 1, 2, 3
+STP_DEBUG_DEPTH, STP_DEBUG_COUNT_PER_PIXEL, STP_DEBUG_TRANSMITTANCE = 4, 5, 6
+_VIS_WITHOUT_LOG = (STP_DEBUG_COUNT_PER_TILE, STP_DEBUG_TRANSMITTANCE)
 
 
-def settings_from_dict(d, blend_record_cap=0, render_depth=False):
+def settings_from_dict(d, blend_record_cap=0, render_depth=False, debug_visualization=0, debug_range=None):
     """dict produced by ExtendedSettings.to_dict() -> StpSettings; every key mandatory like the
-    reference's from_json (rasterizer.h:160-182 uses .at())."""
+    reference's from_json (rasterizer.h:160-182 uses .at()).  render_depth=True is DebugVisualization::Depth
+    (rasterize_points.cu:104-107); the other visualisation types are only reachable through the C / C++ interface in the
+    reference -- here also through the private `debug_visualization` argument of rasterize_gaussians."""
     ss, cs = d["sort_settings"], d["culling_settings"]
     q = ss["queue_sizes"]
+    vis = STP_DEBUG_DEPTH if render_depth else int(debug_visualization or 0)
+    keep_log = int(ss["sort_mode"]) in BLEND_RECORD_MODES or (vis != 0 and vis not in _VIS_WITHOUT_LOG)
+    lo, hi = debug_range if debug_range is not None else (0.0, 10000.0)
     return StpSettings(int(ss["sort_mode"]), int(ss["sort_order"]), int(q["tile_4x4"]), int(q["tile_2x2"]),
                        int(q["per_pixel"]), int(bool(cs["rect_bounding"])), int(bool(cs["tight_opacity_bounding"])),
                        int(bool(cs["tile_based_culling"])), int(bool(cs["hierarchical_4x4_culling"])),
                        int(bool(d["load_balancing"])), int(bool(d["proper_ewa_scaling"])),
-                       int(blend_record_cap) if (int(ss["sort_mode"]) in BLEND_RECORD_MODES or render_depth) else 0,
-                       STP_DEBUG_DEPTH if render_depth else 0)
+                       int(blend_record_cap) if keep_log else 0, vis, int(debug_range is not None), float(lo), float(hi),
+                       0, 0)
 
 
 def _ptr(t):
@@ -272,7 +282,7 @@ class NumRendered:
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
                         degree, campos, prefiltered, settings_dict, render_depth, debug, tile_band=None,
-                        record_blends=True, async_forward=None, _into=None):
+                        record_blends=True, async_forward=None, _into=None, debug_visualization=0, debug_range=None):
     """record_blends (GLOBAL / HIER modes): keep the per-pixel blend log that lets the backward pass replay the blends
     instead of sweeping the tile lists again / repeating the hierarchical re-sort; pass False for inference-only calls (GaussianRasterizer does, when no input requires a gradient).
     async_forward (default: environment STP_ASYNC_FORWARD=1): do not wait for num_rendered inside the call -- the first
@@ -283,9 +293,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     device = means3D.device
     P, H, W = means3D.size(0), int(image_height), int(image_width)
     cap = BLEND_RECORD_CAP if record_blends else 0
-    if render_depth and cap <= 0:  # the depth visualisation is computed from the blend log
+    render_depth = bool(render_depth) or bool(debug_visualization)
+    if render_depth and cap <= 0:  # the visualisations are computed from the blend log
         cap = 256
-    st = settings_from_dict(settings_dict, cap, bool(render_depth))
+    st = settings_from_dict(settings_dict, cap, False, STP_DEBUG_DEPTH if not debug_visualization else debug_visualization,
+                            debug_range) if render_depth else settings_from_dict(settings_dict, cap)
     if P == 0:  # rasterize_points.cu:93
         e8 = torch.empty(0, dtype=torch.uint8, device=device)
         return (0, torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device),
@@ -603,6 +615,13 @@ def timing_summary():
 
 def timing_reset():
     _lib.stp_timing_reset()
+
+
+def last_debug_stats():
+    """(value at the debug pixel, min, max, mean, std) of the raw values of the last debug visualisation"""
+    out = (ctypes.c_float * 5)()
+    _lib.stp_last_debug_stats(out)
+    return tuple(out)
 
 
 def kernel_launches():

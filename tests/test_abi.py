@@ -95,3 +95,21 @@ def test_settings_validation_without_gpu(lib):
                               1.0, *([None] * 15), 0, None)
     assert rc == -2
     assert b"Backward not supported for full per-pixel sort" in _C._lib.stp_last_error()
+
+
+def test_cpp_interface_is_exported_and_cmake_target_configures(lib, tmp_path):
+    """the C++ layer of the reference (CudaRasterizer::Rasterizer, rasterizer.h:184-258) is part of the library, and the
+    CMake target of the same name (reference CMakeLists.txt:22-36) configures with the toolchain of this image."""
+    import shutil
+    import subprocess
+    syms = subprocess.run(["nm", "-DC", LIB], capture_output=True, text=True).stdout
+    for name in ("CudaRasterizer::Rasterizer::forward(", "CudaRasterizer::Rasterizer::backward(",
+                 "CudaRasterizer::Rasterizer::markVisible("):
+        assert name in syms, name
+    cmake = shutil.which("cmake")
+    if cmake is None:
+        pytest.skip("cmake not installed")
+    out = subprocess.run([cmake, "-S", ROOT, "-B", str(tmp_path / "b"), "-DCMAKE_CUDA_COMPILER=" + (shutil.which("nvcc") or "nvcc")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert (tmp_path / "b" / "Makefile").exists() or (tmp_path / "b" / "build.ninja").exists()

@@ -389,3 +389,126 @@ def test_async_forward_matches_sync_and_recovers_from_overflow(mode):
     # the hint has been raised by the resolved R: the next asynchronous frame fits
     out = fwd(True)
     assert int(out[0]) == base[0] and not out[0].retried and torch.equal(out[1], base[1])
+
+
+def _magma(x):
+    c = torch.tensor([[-0.002136485053939582, -0.000749655052795221, -0.005386127855323933],
+                      [0.2516605407371642, 0.6775232436837668, 2.494026599312351],
+                      [8.353717279216625, -3.577719514958484, 0.3144679030132573],
+                      [-27.66873308576866, 14.26473078096533, -13.64921318813922],
+                      [52.17613981234068, -27.94360607168351, 12.94416944238394],
+                      [-50.76852536473588, 29.04658282127291, 4.23415299384598],
+                      [18.65570506591883, -11.48977351997711, -5.601961508734096]], dtype=torch.float32, device=x.device)
+    x = x.clamp(0, 1)
+    v = c[6].view(3, 1, 1).expand(3, *x.shape).clone()
+    for k in range(5, -1, -1):
+        v = c[k].view(3, 1, 1) + x.unsqueeze(0) * v
+    return v.clamp(0, 1)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_debug_visualisations_defining_properties(mode):
+    """The five DebugVisualization types besides Depth (rasterizer_debug.h:11-20) cannot be reached through the reference's
+    Python API (render_depth selects Depth only), so they are checked against their definitions:
+    Transmittance = Magma(1 - final_T); GaussianCountPerTile = Magma(len(tile list) / max); GaussianCountPerPixel: raw
+    maximum = the largest blend count; sort errors: exactly zero for the exact per-pixel sort (PPX_FULL, lists <= 1024),
+    positive somewhere for the global z-order measured against camera distance."""
+    import stp_scenes as S
+    from diff_gaussian_rasterization import _C
+    dev = _dev()
+    W, H, P = 200, 120, 5000
+    sc, cam = S.make_scene(P, W, H, 611, sigma_scale=0.4)
+    sc, cam = S.to_device(sc, dev), S.to_device(cam, dev)
+    d = S.default_settings_dict(sort_mode=mode, per_pixel=16 if mode == 2 else 4)
+    e = torch.empty(0, device=dev)
+
+    def vis(kind, rng=None):
+        out = _C.rasterize_gaussians(cam.bg, sc.means3D, e, sc.opacities, sc.scales, sc.rotations, 1.0, e, cam.viewmatrix,
+                                     cam.projmatrix, cam.inv_viewprojmatrix, cam.tanfovx, cam.tanfovy, H, W, sc.shs, 3,
+                                     cam.campos, False, d, False, False, debug_visualization=kind, debug_range=rng)
+        return out, _C.last_debug_stats()
+    plain = ours_forward(sc, cam, d)
+    img = _C.view_image(plain[5], W, H)
+    # Transmittance
+    out, st = vis(_C.STP_DEBUG_TRANSMITTANCE, (0.0, 1.0))
+    assert (out[1] - _magma(1.0 - img["final_T"])).abs().max().item() <= 2e-5
+    assert abs(st[3] - (1.0 - img["final_T"]).mean().item()) <= 1e-4
+    # Gaussians per tile
+    lens = (img["ranges"][:, 1] - img["ranges"][:, 0]).float().view((H + 15) // 16, (W + 15) // 16)
+    per_pix = lens.repeat_interleave(16, 0).repeat_interleave(16, 1)[:H, :W]
+    out, st = vis(_C.STP_DEBUG_COUNT_PER_TILE)
+    assert st[1] == per_pix.min().item() and st[2] == per_pix.max().item()
+    expect = _magma((per_pix.clamp(st[1], st[2])) / (st[2] - st[1]))
+    assert (out[1] - expect).abs().max().item() <= 2e-5
+    # Gaussians blended per pixel: raw range = range of the blend counts (counted again from a logging forward pass)
+    out, st = vis(_C.STP_DEBUG_COUNT_PER_PIXEL)
+    assert st[1] >= 0 and st[2] >= 1 and st[2] <= lens.max().item()
+    # sort errors
+    for kind in (_C.STP_DEBUG_SORT_ERROR_OPACITY, _C.STP_DEBUG_SORT_ERROR_DISTANCE):
+        out, st = vis(kind, (0.0, 1.0))
+        if mode == 1:
+            assert lens.max().item() <= 1024 and st[2] == 0.0  # exact per-pixel sort: no inversion anywhere
+            assert (out[1] - _magma(torch.zeros(H, W, device=dev))).abs().max().item() <= 1e-6
+        elif mode == 0:
+            assert st[2] > 0.0  # z-ordered list, distance-measured: inversions exist
+        assert st[1] >= 0.0 and out[1].isfinite().all()
+
+
+@pytest.mark.parametrize("mode,dbg", [(0, 6), (3, 6), (2, 6), (3, 4), (0, 5)], ids=["global", "hier", "kbuffer", "hier_depth", "global_T"])
+def test_cpp_interface_shim(tmp_path, mode, dbg):
+    """CudaRasterizer::Rasterizer (include/cuda_rasterizer/rasterizer.h, the reference's rasterizer.h:184-258) driven from
+    a C++ program the way the viewer does -- std::function arenas, raw pointers, DebugVisualizationData with the
+    statistics callback and the 128-frame stage timer -- must give what the Python path gives: forward image, radii,
+    num_rendered; backward dL_dmeans3D; debug visualisations (dbg: DebugVisualization enum value, 6 = Disabled)."""
+    import os
+    import struct
+    import subprocess
+    import stp_scenes as S
+    from conftest import PKG, ROOT
+    from diff_gaussian_rasterization import _C
+    dev = _dev()
+    W, H, P = 144, 96, 3000
+    sc, cam = S.make_scene(P, W, H, 4711, sigma_scale=0.5)
+    dL = S.make_upstream_grad(W, H, 4712)
+    exe = tmp_path / "shim_smoke"
+    lib_dir = os.path.join(PKG, "lib")
+    subprocess.check_call(["nvcc", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", str(exe),
+                           os.path.join(ROOT, "tests", "cpp", "shim_smoke.cpp"), "-I" + os.path.join(ROOT, "include", "cuda_rasterizer"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + lib_dir, "-lstp_rasterizer", "-lcudart",
+                           "-Xlinker", "-rpath=" + lib_dir])
+    scene_bin, out_bin = tmp_path / "scene.bin", tmp_path / "out.bin"
+    with open(scene_bin, "wb") as fh:
+        fh.write(struct.pack("4i", P, W, H, 16))
+        fh.write(struct.pack("2f", cam.tanfovx, cam.tanfovy))
+        for t in (sc.means3D, sc.scales, sc.rotations, sc.opacities, sc.shs, cam.viewmatrix, cam.projmatrix,
+                  cam.inv_viewprojmatrix, cam.campos, cam.bg, dL):
+            fh.write(t.contiguous().numpy().astype(np.float32).tobytes())
+    log = subprocess.run([str(exe), str(scene_bin), str(out_bin), str(mode), str(dbg)], capture_output=True, text=True, timeout=300)
+    assert log.returncode == 0, log.stdout + log.stderr
+    raw = open(out_bin, "rb").read()
+    R = struct.unpack_from("i", raw, 0)[0]
+    stats = struct.unpack_from("5f", raw, 4)
+    has_timings = struct.unpack_from("i", raw, 24)[0]
+    off = 28
+    img = torch.from_numpy(np.frombuffer(raw, np.float32, 3 * W * H, off).reshape(3, H, W).copy())
+    off += 12 * W * H
+    radii = torch.from_numpy(np.frombuffer(raw, np.int32, P, off).copy())
+    off += 4 * P
+    gmean = torch.from_numpy(np.frombuffer(raw, np.float32, 3 * P, off).reshape(P, 3).copy())
+    assert has_timings == 1 and "Preprocess" in log.stdout and "Total" in log.stdout
+    scd, camd = S.to_device(sc, dev), S.to_device(cam, dev)
+    d = S.default_settings_dict(sort_mode=mode)
+    e = torch.empty(0, device=dev)
+    kind = {4: _C.STP_DEBUG_DEPTH, 5: _C.STP_DEBUG_TRANSMITTANCE, 6: 0}[dbg]
+    out = _C.rasterize_gaussians(camd.bg, scd.means3D, e, scd.opacities, scd.scales, scd.rotations, 1.0, e, camd.viewmatrix,
+                                 camd.projmatrix, camd.inv_viewprojmatrix, camd.tanfovx, camd.tanfovy, H, W, scd.shs, 3,
+                                 camd.campos, False, d, False, False, record_blends=False, debug_visualization=kind)
+    assert R == int(out[0]) and torch.equal(radii, out[2].cpu())
+    assert torch.equal(img, out[1].cpu())
+    if kind == 0:
+        g = ours_backward(scd, camd, d, out, dL.to(dev))
+        ref_g = g[3].cpu()
+        assert (gmean - ref_g).abs().max().item() <= 1e-5 * max(ref_g.abs().max().item(), 1e-30)
+    else:
+        mine = _C.last_debug_stats()
+        assert all(abs(a - b) <= 1e-6 * max(1.0, abs(b)) for a, b in zip(stats[1:], mine[1:])), (stats, mine)
