@@ -466,7 +466,8 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     }
     timer.mark("Duplicate");
     if (R > 0) {
-        STP_CUDA(launch_tile_sort(f, g, img, b, host_error_flags(), stream), "tile sort");
+        STP_CUDA(launch_tile_sort(f, g, img, b, colors_precomp != nullptr ? colors_precomp : g.rgb, host_error_flags(), stream),
+                 "tile sort");
         g_launches += sort_kernel_launches();
     }
     timer.mark("Sort");
@@ -475,6 +476,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     ra.ranges = img.ranges;
     ra.point_list = b.point_list;
     ra.slab = b.slab;
+    ra.slab_rgb = b.slab_rgb;
     ra.means2D = g.means2D;
     ra.conic_opacity = g.conic_opacity;
     ra.cov3D_inv = g.cov3D_inv;
@@ -488,6 +490,7 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user, stp_alloc_fn binning_a
     ra.log_overflow = g.counters + 4;
     ra.abort_flag = async ? g.counters + kAbortFlag : nullptr;
     ra.full_sort_ray = false;
+    ra.log_is_position = s.sort_mode == STP_SORT_HIER || s.sort_mode == STP_SORT_PPX_FULL;
     ra.rec_cap = s.rec_cap;
     if (s.sort_mode == STP_SORT_GLOBAL) {
         STP_CUDA(launch_render_global_fwd(f, ra, stream), "render (GLOBAL)");
@@ -588,6 +591,7 @@ int backward_impl(int which, int first, int count, int P, int D, int M, size_t b
         ra.ranges = img.ranges;
         ra.point_list = b.point_list;
         ra.slab = b.slab;
+        ra.slab_rgb = b.slab_rgb;
         ra.means2D = g.means2D;
         ra.conic_opacity = g.conic_opacity;
         ra.cov3D_inv = g.cov3D_inv;

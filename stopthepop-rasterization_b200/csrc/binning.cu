@@ -307,9 +307,11 @@ __device__ __forceinline__ int pow2_at_least(int n) {
 // what the sort epilogue needs to write the tile's slab (stp_slab.cuh); slab == nullptr: index buffers only
 struct SlabSource {
     float4* slab;
+    float4* slab_rgb;
     const float2* means2D;
     const float4* conic_opacity;
     const float4* cov3D_inv;
+    const float* colors;
 };
 struct EmitSorted {  // final outputs: the reference's point_list_keys / point_list, and the slab record of the instance
     uint64_t* keys;
@@ -325,6 +327,8 @@ struct EmitSorted {  // final outputs: the reference's point_list_keys / point_l
             const float4* const inv = src.cov3D_inv + 3 * (size_t)id;
             slab_store(src.slab, first + (uint32_t)i, (int)id, __ldg(src.means2D + id), __ldg(src.conic_opacity + id),
                        __ldg(inv), __ldg(inv + 1), __ldg(inv + 2));
+            const float* const c = src.colors + 3 * (size_t)id;
+            src.slab_rgb[first + (uint32_t)i] = make_float4(__ldg(c), __ldg(c + 1), __ldg(c + 2), __int_as_float((int)id));
         }
     }
 };
@@ -478,7 +482,7 @@ cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const Image
 int sort_kernel_launches() { return 2; }
 
 cudaError_t launch_tile_sort(const Frame& f, const GeometryState& g, const ImageState& img, const BinningState& b,
-                             uint32_t* host_flags, cudaStream_t stream) {
+                             const float* colors, uint32_t* host_flags, cudaStream_t stream) {
     // per call, not cached in a process-wide static: both the attribute and the SM count belong to the CURRENT device
     // (a process may drive several GPUs); the two driver calls cost about a microsecond
     int dev = 0, sm_count = 0;
@@ -486,7 +490,7 @@ cudaError_t launch_tile_sort(const Frame& f, const GeometryState& g, const Image
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(tile_sort_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(kLargeCap * sizeof(uint64_t)));
-    const SlabSource src{b.slab, g.means2D, g.conic_opacity, g.cov3D_inv};
+    const SlabSource src{b.slab, b.slab_rgb, g.means2D, g.conic_opacity, g.cov3D_inv, colors};
     tile_sort_small_kernel<<<f.grid_x * f.grid_y, 256, 0, stream>>>(img.ranges, img.tile_cursor, b.bucket, b.keys,
                                                                     b.point_list, g.counters, src, host_flags);
     tile_sort_large_kernel<<<sm_count, kLargeThreads, kLargeCap * sizeof(uint64_t), stream>>>(

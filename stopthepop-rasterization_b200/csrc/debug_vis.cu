@@ -102,9 +102,11 @@ debug_replay_kernel(Frame f, RenderArgs a, int type, const float* __restrict__ m
                     ray = PIXEL_MAP == 2 && a.full_sort_ray ? view_ray_xloop(cam, (float)px, (float)py) : view_ray(cam, (float)px, (float)py);
                 }
                 float cur = -3.402823466e+38f;
+                const uint32_t first = a.ranges[tile_lin].x;
                 for (uint32_t k = 0; k < n; ++k) {
                     const uint2 r = __ldcs(rec + (size_t)k * 256);
-                    const int id = (int)r.x;
+                    // the log stores the tile-local list position in the slab modes HIER / PPX_FULL, the id otherwise
+                    const int id = a.log_is_position ? __float_as_int(__ldg(a.slab_rgb + first + r.x).w) : (int)r.x;
                     const float alpha = __uint_as_float(r.y);
                     float depth;
                     if constexpr (RAY_DEPTH) {

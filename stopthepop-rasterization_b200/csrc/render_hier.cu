@@ -147,9 +147,7 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
 
     const uint2* __restrict__ ranges = BWD ? ab.ranges : a.ranges;
     const float4* __restrict__ slab = BWD ? ab.slab : a.slab;
-    const float2* __restrict__ means2D = BWD ? ab.means2D : a.means2D;
-    const float4* __restrict__ conic_opacity = BWD ? ab.conic_opacity : a.conic_opacity;
-    const float* __restrict__ colors = BWD ? ab.colors : a.colors;
+    const float4* __restrict__ slab_rgb = BWD ? ab.slab_rgb : a.slab_rgb;
 
     const uint2 range = ranges[tile_lin];
     const uint32_t first = range.x;                      // absolute list position of the tile's first instance
@@ -214,7 +212,8 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     uint32_t rec_idx = (uint32_t)tile_lin * (uint32_t)a.rec_cap * 256u + (uint32_t)tid;
     __syncthreads();  // barriers initialised, rays written (the only CTA barrier before the epilogue)
 
-    // head queue: sorted by depth, hd[0] is the next to blend; hi = Gaussian id
+    // head queue: sorted by depth, hd[0] is the next to blend; hi = tile-local list position (the blend reads colour and
+    // Gaussian id from the {r, g, b, id} slab; the blend log stores the position)
     float hd[HEAD], hs[HEAD];
     int hi[HEAD];
 #pragma unroll
@@ -229,7 +228,7 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     auto blend_one = [&]() {
         --hcount;
         if (!active) return;
-        const int id = hi[0];
+        const uint32_t j = first + (uint32_t)hi[0];
         if constexpr (!BWD) {
             const float alpha = hs[0];
             const float test_T = fmul(T, fsub(1.0f, alpha));
@@ -237,29 +236,33 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
                 active = false;
                 return;
             }
-            C0 = ffma(fmul(__ldg(colors + 3 * id + 0), alpha), T, C0);
-            C1 = ffma(fmul(__ldg(colors + 3 * id + 1), alpha), T, C1);
-            C2 = ffma(fmul(__ldg(colors + 3 * id + 2), alpha), T, C2);
+            const float4 cr = __ldg(slab_rgb + j);
+            C0 = ffma(fmul(cr.x, alpha), T, C0);
+            C1 = ffma(fmul(cr.y, alpha), T, C1);
+            C2 = ffma(fmul(cr.z, alpha), T, C2);
             T = test_T;
             if (a.blend_rec != nullptr) {
                 // streaming store: the log is written once and read by the backward pass much later
                 const uint32_t rec_end = ((uint32_t)tile_lin + 1u) * (uint32_t)a.rec_cap * 256u;
-                if (rec_idx < rec_end) __stcs(a.blend_rec + rec_idx, make_uint2((uint32_t)id, __float_as_uint(alpha)));
+                if (rec_idx < rec_end) __stcs(a.blend_rec + rec_idx, make_uint2((uint32_t)hi[0], __float_as_uint(alpha)));
                 rec_idx += 256u;
             }
         } else {
             const float G = hs[0];
-            const float4 co = __ldg(conic_opacity + id);
+            float4 h0, h1;
+            slab_ldg_head(slab, j, h0, h1);
+            const float4 co = make_float4(h0.z, h0.w, h1.x, h1.y);
             const float alpha = fminf(0.99f, fmul(co.w, G));
             const float test_T = fmul(T, fsub(1.0f, alpha));
             if (test_T < kTThreshold) {
                 active = false;
                 return;
             }
-            const float2 xy = __ldg(means2D + id);
-            const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
+            const float4 cr = __ldg(slab_rgb + j);
+            const int id = __float_as_int(cr.w);
+            const float dx = fsub(h0.x, pxf), dy = fsub(h0.y, pyf);
             const float dchannel_dcolor = alpha * T;
-            const float c0 = __ldg(colors + 3 * id + 0), c1 = __ldg(colors + 3 * id + 1), c2 = __ldg(colors + 3 * id + 2);
+            const float c0 = cr.x, c1 = cr.y, c2 = cr.z;
             C0 += c0 * alpha * T;
             C1 += c1 * alpha * T;
             C2 += c2 * alpha * T;
@@ -574,19 +577,16 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     // insertion step for the held survivor: depth on the pixel's ray (second half of the record), blend the head minimum
     // if the head is full, insert by strict '<'
     auto insert_held = [&]() {
-        const uint32_t j = first + (uint32_t)held;
+        int ei = held;
         held = -1;
-        const float4* const rec = slab + 4 * (size_t)j;
-        const uint32_t sw = slab_swizzle(j);
-        const float4 c1 = __ldg(rec + (1 ^ sw)), c2 = __ldg(rec + (2 ^ sw)), c3 = __ldg(rec + (3 ^ sw));
-        const float ic[6] = {c1.w, c2.x, c2.y, c2.z, c2.w, c3.x};
+        float ic[6], ux, uy, uz;
+        slab_ldg_inv(slab, first + (uint32_t)ei, ic, ux, uy, uz);
         const Vec3 ray{sh.pix_ray[tid], sh.pix_ray[256 + tid], sh.pix_ray[512 + tid]};
-        float e_d = depth_along_ray(ic, c3.y, c3.z, c3.w, ray);
+        float e_d = depth_along_ray(ic, ux, uy, uz, ray);
         if (e_d < 0.0f) return;
         if (hcount >= HEAD) blend_one();
         if (!active) return;
         float e_s = held_s;
-        int ei = __float_as_int(c1.z);
 #pragma unroll
         for (int k = 0; k < HEAD; ++k) {
             if (e_d < hd[k]) {
@@ -741,15 +741,33 @@ blend_replay_bwd_kernel(Frame f, RenderBwdArgs a) {
     const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
     const uint2* __restrict__ rec = a.blend_rec + (size_t)tile_lin * a.rec_cap * 256 + tid;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    // what the log stores per blend: the tile-local list position in the slab modes (HIER / PPX_FULL: geometry and colour
+    // come from the tile's contiguous slabs), the Gaussian id in GLOBAL mode (gathered)
+    const uint32_t first = PIXEL_MAP != 0 ? a.ranges[tile_lin].x : 0u;
     uint2 nxt = __ldcs(rec);
     for (uint32_t k = 0; k < n; ++k) {
         const uint2 cur = nxt;
         if (k + 1 < n) nxt = __ldcs(rec + (size_t)(k + 1) * 256);
-        const int id = (int)cur.x;
         const float alpha = __uint_as_float(cur.y);
-        const float4 co = __ldg(a.conic_opacity + id);
-        const float2 xy = __ldg(a.means2D + id);
-        const float c0 = __ldg(a.colors + 3 * id + 0), c1 = __ldg(a.colors + 3 * id + 1), c2 = __ldg(a.colors + 3 * id + 2);
+        int id;
+        float4 co;
+        float2 xy;
+        float c0, c1, c2;
+        if constexpr (PIXEL_MAP != 0) {
+            const uint32_t j = first + cur.x;
+            float4 h0, h1;
+            slab_ldg_head(a.slab, j, h0, h1);
+            const float4 cr = __ldg(a.slab_rgb + j);
+            xy = make_float2(h0.x, h0.y);
+            co = make_float4(h0.z, h0.w, h1.x, h1.y);
+            c0 = cr.x; c1 = cr.y; c2 = cr.z;
+            id = __float_as_int(cr.w);
+        } else {
+            id = (int)cur.x;
+            co = __ldg(a.conic_opacity + id);
+            xy = __ldg(a.means2D + id);
+            c0 = __ldg(a.colors + 3 * id + 0); c1 = __ldg(a.colors + 3 * id + 1); c2 = __ldg(a.colors + 3 * id + 2);
+        }
         const float dx = fsub(xy.x, pxf), dy = fsub(xy.y, pyf);
         const float G = (alpha < 0.99f) ? alpha / co.w : expf(gaussian_power(dx, dy, co.x, co.y, co.z));
         const float test_T = fmul(T, fsub(1.0f, alpha));

@@ -363,12 +363,14 @@ __device__ __forceinline__ bool full_fast_sort_blend(const FullFastShared& sh, i
         const int e = r * 32 + lane;
         const uint32_t mykey = (uint32_t)(v[r] >> 32);
         float alpha = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
-        int id = -1;
+        const int idx = (int)((uint32_t)v[r] & 1023u);  // tile-local list position: what the blend log stores
         if (e < S) {
-            slab_alpha(sh.slab, (int)((uint32_t)v[r] & 1023u), first, pxf, pyf, alpha, id);  // passed before: same bits
-            w0 = fmul(__ldg(a.colors + 3 * id + 0), alpha);
-            w1 = fmul(__ldg(a.colors + 3 * id + 1), alpha);
-            w2 = fmul(__ldg(a.colors + 3 * id + 2), alpha);
+            int id;
+            slab_alpha(sh.slab, idx, first, pxf, pyf, alpha, id);  // passed before: same bits
+            const float4 cr = __ldg(a.slab_rgb + first + (uint32_t)idx);
+            w0 = fmul(cr.x, alpha);
+            w1 = fmul(cr.y, alpha);
+            w2 = fmul(cr.z, alpha);
         }
         const int cnt = min(32, S - r * 32);
         float myT = 0.f;
@@ -399,7 +401,7 @@ __device__ __forceinline__ bool full_fast_sort_blend(const FullFastShared& sh, i
             have_last = true;
             if (logging) {
                 if (lane < stop && nrec + (uint32_t)lane < (uint32_t)a.rec_cap)
-                    __stcs(a.blend_rec + rec_first + (nrec + (uint32_t)lane) * 256u, make_uint2((uint32_t)id, __float_as_uint(alpha)));
+                    __stcs(a.blend_rec + rec_first + (nrec + (uint32_t)lane) * 256u, make_uint2((uint32_t)idx, __float_as_uint(alpha)));
                 nrec += (uint32_t)stop;
             }
         }
@@ -586,8 +588,7 @@ render_full_kernel(Frame f, RenderArgs a) {
                     if (e < lim && v[r] >= 0) {
                         float4 h0, h1;
                         slab_ldg_head(a.slab, range.x + (uint32_t)(v[r] >> 10), h0, h1);
-                        const int id = __float_as_int(h1.z);
-                        my_id = id;
+                        my_id = v[r] >> 10;  // tile-local list position: what the blend log stores
                         const float dx = fsub(h0.x, pxf), dy = fsub(h0.y, pyf);
                         const float pw = opacity_factor(dx, dy, h0.z, h0.w, h1.x);
                         if (!(pw < 0.0f)) {
@@ -595,9 +596,10 @@ render_full_kernel(Frame f, RenderArgs a) {
                             accept = !(alpha < kAlphaThreshold);
                         }
                         if (accept) {
-                            c0 = __ldg(a.colors + 3 * id + 0);
-                            c1 = __ldg(a.colors + 3 * id + 1);
-                            c2 = __ldg(a.colors + 3 * id + 2);
+                            const float4 cr = __ldg(a.slab_rgb + range.x + (uint32_t)my_id);
+                            c0 = cr.x;
+                            c1 = cr.y;
+                            c2 = cr.z;
                         }
                     }
                     uint32_t m = __ballot_sync(0xffffffffu, accept);

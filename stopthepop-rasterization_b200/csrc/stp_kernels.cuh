@@ -25,6 +25,7 @@ struct RenderArgs {
     const uint2* ranges;
     const uint32_t* point_list;
     const float4* slab;   // per-tile slabs in list order (stp_slab.cuh), nullptr in GLOBAL mode
+    const float4* slab_rgb;  // {r, g, b, id} per instance, list order
     const float2* means2D;
     const float4* conic_opacity;
     const float4* cov3D_inv;
@@ -32,12 +33,14 @@ struct RenderArgs {
     float* final_T;
     uint32_t* n_contrib;
     float* out_color;
-    uint2* blend_rec;      // blend log (nullptr = do not record)
+    uint2* blend_rec;      // blend log (nullptr = do not record): (entry, alpha) per blend, entry = tile-local list
+                           // position in the slab modes HIER / PPX_FULL, Gaussian id in GLOBAL / PPX_KBUFFER
     uint32_t* blend_count;
     uint32_t* tile_flags;
     uint32_t* log_overflow;  // counter: pixels whose log overflowed in a mode without list-driven backward (PPX_FULL)
     const uint32_t* abort_flag;  // non-zero: the binning arena of this (asynchronous) frame was too small -- render nothing
     bool full_sort_ray;          // debug visualisation of PPX_FULL: depths on the ray as that mode's kernels round it
+    bool log_is_position;        // the blend log holds tile-local list positions (HIER / PPX_FULL), not Gaussian ids
     int rec_cap;
 };
 
@@ -45,6 +48,7 @@ struct RenderBwdArgs {
     const uint2* ranges;
     const uint32_t* point_list;
     const float4* slab;
+    const float4* slab_rgb;
     const float2* means2D;
     const float4* conic_opacity;
     const float4* cov3D_inv;
@@ -142,7 +146,7 @@ cudaError_t launch_tile_scan(const Frame& f, const GeometryState& g, const Image
 cudaError_t launch_duplicate(int P, const Frame& f, const Settings& s, const GeometryState& g, const int* radii,
                              const ImageState& img, const BinningState& b, size_t cap, cudaStream_t stream);
 cudaError_t launch_tile_sort(const Frame& f, const GeometryState& g, const ImageState& img, const BinningState& b,
-                             uint32_t* host_flags, cudaStream_t stream);
+                             const float* colors, uint32_t* host_flags, cudaStream_t stream);
 
 // render_global.cu
 cudaError_t launch_render_global_fwd(const Frame& f, const RenderArgs& a, cudaStream_t stream);

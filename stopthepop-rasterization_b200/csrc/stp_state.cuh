@@ -91,7 +91,7 @@ struct ImageState {
     }
 };
 
-// per-instance arena: 28 B/instance (+64 B with slabs).  point_list / keys are the sorted outputs (the reference's
+// per-instance arena: 28 B/instance (+80 B with slabs).  point_list / keys are the sorted outputs (the reference's
 // point_list / point_list_keys, rasterizer_impl.h:57-67); bucket holds the unsorted
 // (depth bits << 32 | Gaussian index) records grouped by tile, scratch is the ping-pong buffer of the
 // global merge passes that only tiles longer than the in-smem capacity need; slab holds one 64-byte record per
@@ -105,7 +105,8 @@ struct BinningState {
     uint64_t* keys;
     uint64_t* bucket;
     uint64_t* scratch;
-    float4* slab;  // nullptr unless requested
+    float4* slab;      // nullptr unless requested
+    float4* slab_rgb;  // [cap] {r, g, b, Gaussian id (bits)} in list order: what a blend needs besides the geometric record
     static BinningState from_chunk(char*& chunk, size_t cap, bool with_slab) {
         BinningState b;
         cap = binning_round_cap(cap);
@@ -114,10 +115,14 @@ struct BinningState {
         obtain(chunk, b.bucket, cap);
         obtain(chunk, b.scratch, cap);
         b.slab = nullptr;
-        if (with_slab) obtain(chunk, b.slab, cap * 4);
+        b.slab_rgb = nullptr;
+        if (with_slab) {
+            obtain(chunk, b.slab, cap * 4);
+            obtain(chunk, b.slab_rgb, cap);
+        }
         return b;
     }
-    static size_t bytes_per_instance(bool with_slab) { return 4 + 8 + 8 + 8 + (with_slab ? 64 : 0); }
+    static size_t bytes_per_instance(bool with_slab) { return 4 + 8 + 8 + 8 + (with_slab ? 64 + 16 : 0); }
 };
 
 template <typename T, typename... A>

@@ -75,7 +75,7 @@ def test_abi_version_and_arena_sizes(lib):
             assert lib.stp_binning_capacity(nbytes, ref) == rounded
             assert lib.stp_binning_bytes(rounded, ref) == nbytes
     assert (lib.stp_binning_bytes(6400, ctypes.addressof(hier)) - lib.stp_binning_bytes(6400, ctypes.addressof(glob))
-            == 64 * 6400)
+            == (64 + 16) * 6400)  # geometric slab record + {r, g, b, id}
 
 
 def test_settings_validation_without_gpu(lib):

@@ -26,9 +26,11 @@ with open(out_csv, "w", newline="") as fh:
 print(open(out_csv).read()[:3000])
 if len(sys.argv) > 4:
     wl, tj = sys.argv[3], sys.argv[4]
+    # (order matters: the first match wins -- preprocess_bwd before preprocess_kernel is not needed, names differ)
     stage_of = {"preprocess_kernel": "Preprocess", "tile_scan": "Preprocess", "duplicate_kernel": "Duplicate",
                 "tile_sort": "Sort", "render_global_fwd": "Render", "render_global_bwd": "RenderBackward",
-                "render_hier_kernel": "Render", "render_hier_replay": "RenderBackward", "preprocess_bwd": "PreprocessBackward"}
+                "render_hier_kernel": "Render", "blend_replay_bwd": "RenderBackward", "render_full": "Render",
+                "render_kbuffer": "Render", "preprocess_bwd": "PreprocessBackward"}
     ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     ii, ti = hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active"), hdr.index("gpu__time_duration.sum")
     acc, cnt, issue = {}, {}, {}
