@@ -113,3 +113,25 @@ def test_cpp_interface_is_exported_and_cmake_target_configures(lib, tmp_path):
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert (tmp_path / "b" / "Makefile").exists() or (tmp_path / "b" / "build.ninja").exists()
+
+
+def test_settings_struct_is_the_same_in_header_binding_and_integration_doc():
+    """StpSettings is passed by pointer: a binding whose struct is shorter than the header's makes the library read
+    garbage (the INTEGRATION.md snippet had gone stale).  Header, ctypes binding and the documented stub
+    must list the same fields in the same order."""
+    from diff_gaussian_rasterization import _C
+    src = open(HEADER).read()
+    body = src[src.index("typedef struct StpSettings {"):src.index("} StpSettings;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in re.findall(r"(int32_t|float)\s+([^;]+);", body):
+        for name in decl[1].split(","):
+            fields.append((name.strip(), decl[0]))
+    binding = [(n, "float" if t is ctypes.c_float else "int32_t") for n, t in _C.StpSettings._fields_]
+    assert binding == fields
+    assert ctypes.sizeof(_C.StpSettings) == 4 * len(fields)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = doc[doc.index("class StpSettings(ctypes.Structure):"):doc.index("assert lib.stp_abi_version()")]
+    doc_fields = re.findall(r'"([a-z_0-9A-Z]+)"', stub)
+    assert doc_fields == [n for n, _ in fields]
+    assert f"stp_abi_version() == {_C._lib.stp_abi_version()}" in doc
