@@ -339,7 +339,7 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
             nd[o] = __shfl_sync(qmask, my_d, o, 4);
-            rank += (o != p) && (nd[o] < my_d || (nd[o] == my_d && o < p));
+            rank += (o < p) ? (nd[o] <= my_d) : (nd[o] < my_d);  // ties by position; o == p: my own entry, never counted
         }
         // final position of my new entry: rank + #resident <= it (resident first on ties)
         int pos_new = rank;
@@ -487,7 +487,7 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
                 const float dj = nwd[j];
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    rk_new[t] += (dj < e_d[t]) || (dj == e_d[t] && j < cpos[t]);
+                    rk_new[t] += (j < cpos[t]) ? (dj <= e_d[t]) : (dj < e_d[t]);  // ties by list position
                     sh_res[t] += dj < r_d[t];
                 }
             }
