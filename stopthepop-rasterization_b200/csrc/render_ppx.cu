@@ -6,8 +6,8 @@
 // K-buffer: one thread per pixel keeps a depth-sorted window of W candidates in registers; a candidate
 // enters only after passing the alpha test and the depth-along-ray >= 0 test, and the window minimum is
 // blended whenever the window is full.  The tile list is staged through shared memory 256 entries at a
-// time (xy + conic/opacity + id); the 48-byte inverse covariance is fetched only for candidates that
-// survive the alpha test.
+// time from the tile's slab (stp_slab.cuh: xy + conic/opacity + id, contiguous in list order); the depth half of the
+// record (inverse covariance) is read only for candidates that survive the alpha test.
 //
 // Full sort: the reference sorts, for EVERY pixel, a sliding window of 4x256 list entries by the pixel's
 // ray depth with a CTA-wide radix sort and lets one thread blend (256 pixels serially per CTA).  Here one
@@ -26,13 +26,6 @@ namespace {
 
 constexpr float kFltMax = 3.402823466e+38f;
 constexpr int kBlock = 256;
-
-__device__ __forceinline__ void load_inv(const float4* __restrict__ inv, int id, float* ic, float& ux, float& uy, float& uz) {
-    const float4 a = __ldg(inv + 3 * id), b = __ldg(inv + 3 * id + 1), c = __ldg(inv + 3 * id + 2);
-    ic[0] = a.x; ic[1] = a.y; ic[2] = a.z;
-    ic[3] = b.x; ic[4] = b.y; ic[5] = b.z;
-    ux = c.x; uy = c.y; uz = c.z;
-}
 
 // ================================================= k-buffer ==========================================================
 template <int WIN, bool BWD>
@@ -54,10 +47,9 @@ render_kbuffer_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     const size_t plane = (size_t)f.W * f.H;
 
     const uint2* __restrict__ ranges = BWD ? ab.ranges : a.ranges;
-    const uint32_t* __restrict__ point_list = BWD ? ab.point_list : a.point_list;
+    const float4* __restrict__ slab = BWD ? ab.slab : a.slab;
     const float2* __restrict__ means2D = BWD ? ab.means2D : a.means2D;
     const float4* __restrict__ conic_opacity = BWD ? ab.conic_opacity : a.conic_opacity;
-    const float4* __restrict__ cov3D_inv = BWD ? ab.cov3D_inv : a.cov3D_inv;
     const float* __restrict__ colors = BWD ? ab.colors : a.colors;
 
     const RayCam cam = make_raycam(f.inv_viewproj, f.cam_pos, f.W, f.H);
@@ -160,13 +152,12 @@ render_kbuffer_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     for (int r = 0; r < rounds; ++r, todo -= kBlock) {
         if (__syncthreads_and(done)) break;
         const uint32_t src = range.x + r * kBlock + tid;
-        if (src < range.y) {
-            const int id = (int)__ldg(point_list + src);
-            s_id[tid] = id;
-            if (id >= 0) {
-                s_xy[tid] = __ldg(means2D + id);
-                s_co[tid] = __ldg(conic_opacity + id);
-            }
+        if (src < range.y) {  // the alpha-test half of the tile's slab record: contiguous, no gather through the id
+            float4 c0, c1;
+            slab_ldg_head(slab, src, c0, c1);
+            s_id[tid] = __float_as_int(c1.z);
+            s_xy[tid] = make_float2(c0.x, c0.y);
+            s_co[tid] = make_float4(c0.z, c0.w, c1.x, c1.y);
         }
         __syncthreads();
         const int n = min(kBlock, todo);
@@ -192,7 +183,7 @@ render_kbuffer_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             const float alpha = fminf(0.99f, fmul(co.w, G));
             if (alpha < kAlphaThreshold) continue;
             float ic[6], ux, uy, uz;
-            load_inv(cov3D_inv, id, ic, ux, uy, uz);
+            slab_ldg_inv(slab, range.x + (uint32_t)(r * kBlock + j), ic, ux, uy, uz);
             const float depth = depth_along_ray(ic, ux, uy, uz, ray);
             if (depth < 0.0f) continue;
             float ed = depth, es = BWD ? G : alpha;

@@ -430,7 +430,7 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
             if sync_group is None:
                 rc = _lib.stp_backward(*args)
             elif tile_band is not None:
-                rc = _backward_band_exchange(args, P, grad_accum, sync_group, device, int(sync_chunks))
+                rc = _backward_band_exchange(args, P, grad_accum, sync_group, device, BAND_SYNC_CHUNKS)
             else:
                 rc = _backward_overlapped(args, P, M, dL_dsh, flat[offs[1]:offs[5]], sync_group,
                                           int(sync_chunks), device)
@@ -487,14 +487,20 @@ def _backward_overlapped(args, P, M, dL_dsh, small, group, chunks, device):
     return 0
 
 
-def _backward_band_exchange(args, P, grad_accum, group, device, chunks=4):
+# ranges of Gaussians the accumulator exchange of tile-band sharding is split into (see _backward_band_exchange).
+# Measured on 8 B200s (C3b, profiles/r02_band_exchange_chunks.txt): 1 range 3.22 ms/step, 2 ranges 3.44, 4 ranges 3.58 --
+# one 192 MB NVLS all-reduce beats pipelining it with the 0.5 ms preprocess-backward stage in smaller messages.
+BAND_SYNC_CHUNKS = int(os.environ.get("STP_BAND_SYNC_CHUNKS", "1"))
+
+
+def _backward_band_exchange(args, P, grad_accum, group, device, chunks=1):
     """tile-band sharding (one view, bands of tile rows per rank): the per-Gaussian backward is linear in the packed
     screen-space gradients, and every rank holds the geometry state of every visible Gaussian (visibility does not
     depend on the band, preprocess.cu), so the ONE exchange is an all-reduce of the 48 B/Gaussian accumulator between
     the render-backward and the preprocess-backward stage -- 5x less than the 236 B/Gaussian of parameter gradients
      -- after which every rank finishes the same preprocess-backward and holds the full gradients.
-    The exchange is pipelined with that stage: the accumulator is reduced in `chunks` ranges of Gaussians on a side
-    stream, and the preprocess-backward of a range starts as soon as its sum has arrived."""
+    The accumulator can be reduced in `chunks` ranges of Gaussians on a side stream, the preprocess-backward of a range
+    starting as soon as its sum has arrived; the default is ONE all-reduce (see BAND_SYNC_CHUNKS)."""
     import torch.distributed as dist
     rc = _lib.stp_backward_render(*args)
     if rc != 0:
