@@ -80,8 +80,9 @@ struct HierShared {
     static constexpr int kMidCap = MID - 4;       // resident entries after a pop
     static constexpr int kMidStride = MID - 3;    // odd stride: the 8 quads of a warp hit distinct banks
     float4 slab[kStages][kBatch * kSlabChunks];   // TMA destination, 2 KB per stage
-    uint64_t full[kStages];                       // mbarrier per stage: the batch has landed
-    uint32_t released[kStages];                   // warps that are done with the stage's current batch
+    uint64_t full[kStages];                       // mbarrier per stage: the batch has landed (armed with expect_tx)
+    uint64_t empty[kStages];                      // mbarrier per stage: all eight warps have read the batch
+    uint32_t released[kStages];                   // elects the warp that arrives last (it refills the stage)
     float tail_d[16 * kTailStride];
     int tail_id[16 * kTailStride];
     float new_d[16 * 48];  // 32 entries per block, stride 48 (16-bank offset between the blocks of a warp)
@@ -161,10 +162,26 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
         mbar_expect_tx(&sh.full[s], bytes);
         bulk_g2s(sh.slab[s], slab + (size_t)kSlabChunks * (first + (uint32_t)k * kBatch), bytes, &sh.full[s]);
     };
+    // A warp is done reading batch k: it arrives on the stage's "empty" mbarrier (release); the warp that arrives last --
+    // elected through a counter -- waits for that phase to complete (acquire: every warp's reads of the stage have been
+    // performed), then re-arms the "full" barrier and issues the bulk copy of batch k + kStages into the stage.
+    auto release_stage = [&](int k) {
+        const int s = k % kStages;
+        mbar_arrive(&sh.empty[s]);  // every thread that read the stage arrives itself (256 arrivals per phase)
+        __syncwarp();
+        if (lane == 0) {
+            if (atomicAdd(&sh.released[s], 1u) == kWarps - 1) {
+                sh.released[s] = 0u;
+                mbar_wait(&sh.empty[s], (uint32_t)(k / kStages) & 1u);
+                if (k + kStages < nb) request_batch(k + kStages);
+            }
+        }
+    };
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&sh.full[s], 1);
+            mbar_init(&sh.empty[s], kWarps * 32);
             sh.released[s] = 0u;
         }
         mbar_fence_init();
@@ -447,15 +464,7 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             e_id[t] = (d == kFltMax) ? -1 : e;
         }
         // this warp is done with the stage: the last of the eight warps re-arms it with batch k + kStages
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            if (atomicAdd(&sh.released[s], 1u) == kWarps - 1) {
-                sh.released[s] = 0u;
-                __threadfence_block();
-                if (k + kStages < nb) request_batch(k + kStages);
-            }
-        }
+        release_stage(k);
         // with 4x4 culling only a few of the 32 entries survive: compact them (list order kept) into new_d/new_id so
         // that every later step costs O(valid) instead of O(32)
         constexpr bool COMPACT = CULL && STP_HIER_COMPACT;
@@ -692,17 +701,8 @@ render_hier_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
     // ---- leave the slab ring in order: a warp that stops early still has to release every remaining batch (the other
     // warps' refills wait for all eight), and no bulk copy may be in flight when the CTA exits -----------------------------
     for (; k < nb; ++k) {
-        const int s = k % kStages;
-        mbar_wait(&sh.full[s], (uint32_t)(k / kStages) & 1u);
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            if (atomicAdd(&sh.released[s], 1u) == kWarps - 1) {
-                sh.released[s] = 0u;
-                __threadfence_block();
-                if (k + kStages < nb) request_batch(k + kStages);
-            }
-        }
+        mbar_wait(&sh.full[k % kStages], (uint32_t)(k / kStages) & 1u);
+        release_stage(k);
     }
 }
 
