@@ -378,15 +378,17 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
                                  cov3D_precomp, viewmatrix, projmatrix, inv_viewprojmatrix, tan_fovx, tan_fovy,
                                  pixel_colors, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
                                  imageBuffer, settings_dict, debug, tile_band=None, want_param_slab=False,
-                                 sync_group=None, sync_chunks=4):
+                                 sync_group=None, sync_chunks=None):
     """sync_group (ours only): a torch.distributed process group over which the gradients are summed before they are
     returned (data-parallel training: views or tile bands sharded across GPUs).
-    Views (no tile_band): the five PARAMETER gradients are all-reduced, overlapped with the computation: the
-    preprocess-backward stage runs in `sync_chunks` ranges of Gaussians and the all-reduce of each range's SH-gradient
-    rows (81 % of the bytes) starts on a side stream as soon as the range is done; only the last range and the small
-    arrays remain exposed.
+    Views (no tile_band): the five PARAMETER gradients are all-reduced -- by default as ONE message, the contiguous
+    parameter-gradient slab; with sync_chunks > 1 overlapped with the computation: the preprocess-backward stage runs in
+    `sync_chunks` ranges of Gaussians and the all-reduce of each range's SH-gradient rows (81 % of the bytes) starts on a
+    side stream as soon as the range is done (measured slower on NVSwitch, see VIEW_SYNC_CHUNKS).
     Tile bands (tile_band given): the packed screen-space accumulator (48 B/Gaussian) is all-reduced between the two
     backward stages instead (_backward_band_exchange); all eight returned gradients are then the full-frame ones."""
+    if sync_chunks is None:
+        sync_chunks = VIEW_SYNC_CHUNKS
     if isinstance(R, NumRendered):  # asynchronous forward: look at num_rendered now; a frame that did not fit was re-run
         R.resolve()
         if R.buffers is not None:
@@ -431,6 +433,11 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
                 rc = _lib.stp_backward(*args)
             elif tile_band is not None:
                 rc = _backward_band_exchange(args, P, grad_accum, sync_group, device, BAND_SYNC_CHUNKS)
+            elif int(sync_chunks) <= 1:
+                rc = _lib.stp_backward(*args)
+                if rc == 0:
+                    import torch.distributed as dist
+                    dist.all_reduce(param_slab, group=sync_group)  # sh | means3D | scales | rot | opacity: one message
             else:
                 rc = _backward_overlapped(args, P, M, dL_dsh, flat[offs[1]:offs[5]], sync_group,
                                           int(sync_chunks), device)
@@ -487,6 +494,11 @@ def _backward_overlapped(args, P, M, dL_dsh, small, group, chunks, device):
     return 0
 
 
+# view sharding: ranges of Gaussians whose SH-gradient rows are all-reduced while the next range is computed; 1 = ONE
+# all-reduce of the whole contiguous parameter-gradient slab after the backward pass.  Measured on 4 B200s (C2, one view per
+# rank, profiles/r02_view_exchange_chunks.txt): 1 -> 2.317 ms/step (e2e 2.74), 2 -> 2.361 (2.85), 4 -> 2.364 (2.94): the
+# 0.15 ms preprocess-backward stage is too short to hide anything, and one large NVLS message moves faster than five.
+VIEW_SYNC_CHUNKS = int(os.environ.get("STP_VIEW_SYNC_CHUNKS", "1"))
 # ranges of Gaussians the accumulator exchange of tile-band sharding is split into (see _backward_band_exchange).
 # Measured on 8 B200s (C3b, profiles/r02_band_exchange_chunks.txt): 1 range 3.22 ms/step, 2 ranges 3.44, 4 ranges 3.58 --
 # one 192 MB NVLS all-reduce beats pipelining it with the 0.5 ms preprocess-backward stage in smaller messages.
