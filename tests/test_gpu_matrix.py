@@ -512,3 +512,47 @@ def test_cpp_interface_shim(tmp_path, mode, dbg):
     else:
         mine = _C.last_debug_stats()
         assert all(abs(a - b) <= 1e-6 * max(1.0, abs(b)) for a, b in zip(stats[1:], mine[1:])), (stats, mine)
+
+
+def test_band_exchange_path_matches_plain_backward(golden):
+    """tile-band sharding with sync_group: render backward, all-reduce of the packed screen-space accumulator, then the
+    preprocess backward (_C._backward_band_exchange), in 1 and in 3 pipelined ranges.  With a one-rank NCCL group and a
+    band that covers the whole image the result must equal the monolithic backward."""
+    import torch.distributed as dist
+    from diff_gaussian_rasterization import _C
+    f = golden("hier_preset")
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29534", rank=0, world_size=1, device_id=_dev())
+        created = True
+    try:
+        dev = _dev()
+        s = f.scene
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        e = torch.empty(0, device=dev)
+        m3, sc, ro, op, sh = t(s["means3D"]), t(s["scales"]), t(s["rotations"]), t(s["opacities"]), t(f.shs())
+        vm, pm, iv, cp, bg = t(s["viewmatrix"]), t(s["projmatrix"]), t(s["inv_viewprojmatrix"]), t(s["campos"]), t(s["bg"])
+        tx, ty = float(s["tanfovx"]), float(s["tanfovy"])
+        band = (0, (f.H + 15) // 16)
+        out = _C.rasterize_gaussians(bg, m3, e, op, sc, ro, 1.0, e, vm, pm, iv, tx, ty, f.H, f.W, sh, f.deg, cp, False,
+                                     f.settings, False, False, tile_band=band)
+        dL = t(s["dL_dout"])
+
+        def bwd(**kw):
+            return _C.rasterize_gaussians_backward(bg, m3, out[2], op, e, sc, ro, 1.0, e, vm, pm, iv, tx, ty, out[1], dL, sh,
+                                                   f.deg, cp, out[3], out[0], out[4], out[5], f.settings, False,
+                                                   tile_band=band, **kw)
+        plain = bwd()
+        saved = _C.BAND_SYNC_CHUNKS
+        try:
+            for chunks in (1, 3):
+                _C.BAND_SYNC_CHUNKS = chunks
+                over = bwd(sync_group=dist.group.WORLD)
+                torch.cuda.synchronize()
+                for a, b in zip(plain, over):
+                    assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-30)
+        finally:
+            _C.BAND_SYNC_CHUNKS = saved
+    finally:
+        if created:
+            dist.destroy_process_group()
