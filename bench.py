@@ -178,6 +178,22 @@ KERNEL_OF_STAGE = {"Preprocess": "preprocess_kernel", "Duplicate": "duplicate_ke
                    "PreprocessBackward": "preprocess_bwd_kernel"}
 
 
+def kernel_name(stage, settings):
+    """the kernel(s) behind a stage for these settings (names as they appear in the ncu captures under profiles/)"""
+    ss = settings["sort_settings"]
+    mode, q = ss["sort_mode"], ss["queue_sizes"]
+    cull = int(bool(settings["culling_settings"]["hierarchical_4x4_culling"]))
+    if stage == "Render":
+        return {0: "render_global_fwd_kernel", 1: "render_full_fast_kernel (+ render_full_kernel for lists > 1024)",
+                2: f"render_kbuffer_kernel<{q['per_pixel']},fwd>",
+                3: f"render_hier_kernel<{q['per_pixel']},{q['tile_2x2']},{cull},0>"}[mode]
+    if stage == "RenderBackward":
+        return {0: "render_global_bwd_kernel", 1: "blend_replay_bwd_kernel<2,0>",
+                2: f"render_kbuffer_kernel<{q['per_pixel']},bwd>",
+                3: "blend_replay_bwd_kernel<1,0> (+ render_hier_kernel<..,1> for pixels whose log overflowed)"}[mode]
+    return KERNEL_OF_STAGE[stage]
+
+
 TRACE_STEPS = False
 MIN_WARM_S = 0.4  # the W warm-up steps are extended to at least this long (SM clocks ramp up from idle)
 STEP_TRACE = []  # --trace-steps: per-step event times of every timed region (diagnostics, adds one event per step)
@@ -564,7 +580,7 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
         res["gpu_launches"] = int(launches)
         if full:
             res["roofline"] = {
-                "bound": "hbm", "kernel": KERNEL_OF_STAGE[dom], "stage": dom,
+                "bound": "hbm", "kernel": kernel_name(dom, settings), "stage": dom,
                 "achieved": per_stage[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": per_stage[dom]["GBps"] / peak, "traffic": measured.get(dom),
                 "traffic_source": (prof.get("_source", "committed ncu capture under profiles/") if measured.get(dom)

@@ -21,7 +21,8 @@
 //   Data movement.  The tile's Gaussians are not gathered through their ids: the tile-sort epilogue has
 //   written one 64-byte record per instance in list order (stp_slab.cuh).  The tail stage reads them from
 //   a shared-memory ring that is filled 32 records (2 KB) at a time with bulk-async copies (TMA,
-//   cp.async.bulk + mbarrier), shared by the eight warps of the tile; the queues carry tile-local list
+//   cp.async.bulk + mbarrier: "full" barriers armed with the byte count, "empty" barriers on which every
+//   reading thread arrives), shared by the eight warps of the tile; the queues carry tile-local list
 //   positions, and the mid / head stages read "their" record from the (L1/L2-resident) slab.
 //   Queues.  One warp owns two 4x4 blocks (one per half-warp); all queue manipulation is rank based
 //   (every lane computes the final position of "its" entries with branch-free counting / binary search

@@ -27,19 +27,6 @@ constexpr int kSlabRecordBytes = 64;
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t slab_swizzle(uint32_t j) { return (j >> 1) & 3u; }
 
-// the four logical chunks of one record, read from `base` (global or shared) where record j of the run starts at
-// float4 index 4 * (j - first); the swizzle is a function of the ABSOLUTE instance index j
-struct SlabRec {
-    float4 c0, c1, c2, c3;
-    __device__ __forceinline__ float2 xy() const { return make_float2(c0.x, c0.y); }
-    __device__ __forceinline__ float4 conic_opacity() const { return make_float4(c0.z, c0.w, c1.x, c1.y); }
-    __device__ __forceinline__ int id() const { return __float_as_int(c1.z); }
-    __device__ __forceinline__ void inv(float* ic, float& ux, float& uy, float& uz) const {
-        ic[0] = c1.w; ic[1] = c2.x; ic[2] = c2.y; ic[3] = c2.z; ic[4] = c2.w; ic[5] = c3.x;
-        ux = c3.y; uy = c3.z; uz = c3.w;
-    }
-};
-
 __device__ __forceinline__ void slab_store(float4* __restrict__ slab, uint32_t j, int id, float2 xy, float4 co, float4 ia,
                                            float4 ib, float4 ic) {
     float4* const r = slab + 4 * (size_t)j;
