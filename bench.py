@@ -10,7 +10,7 @@ Default workload = the configuration north_star's target is quoted on (BASELINE.
 N>1 (default sharding of C3a / C3b / C4): ONE frame, tile-row bands sharded across the ranks (north_star: "sharding
 screen-space tile ranges ... >= 6x aggregate at 8 GPUs tile-sharded"): every rank holds the same Gaussians,
 preprocesses all of them, bins / sorts / renders only its band (bands balanced by the instance counts of a warm-up
-frame); exchange = ONE NCCL all-gather of the image bands (forward) and ONE all-reduce of the 48 B/Gaussian packed
+frame); exchange = ONE NCCL all-gather of the image bands (forward) and ONE all-reduce of the 36 B/Gaussian packed
 screen-space gradient accumulator (backward), after which every rank finishes the per-Gaussian backward and holds the
 full gradients.  Total work is fixed => "scaling": "strong".
 --sharding views (default of C2 / C5): one camera per rank (yaw = rank * 0.08 rad), ONE logical all-reduce of the
@@ -518,7 +518,7 @@ def measure(a, workload, world, rank, dev, steps, warmup, full):
                     "the 1-GPU reference number as the baseline of the tile-sharded configurations)")
     elif bands is not None:
         sharding = (f"tile-row bands of one view ({a.bands}: {bands}); replicated Gaussians, NCCL all-gather of the image "
-                    "bands + all-reduce of the 48 B/Gaussian screen-space gradient accumulator between the two backward "
+                    "bands + all-reduce of the 36 B/Gaussian screen-space gradient accumulator between the two backward "
                     "stages")
     else:
         sharding = ("views (one camera per rank, replicated Gaussians, NCCL all-reduce of parameter grads, overlapped "

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define STP_ABI_VERSION 6
+#define STP_ABI_VERSION 7
 
 /* replaces: enum SortMode / GlobalSortOrder, rasterizer.h:27-41 */
 enum { STP_SORT_GLOBAL = 0, STP_SORT_PPX_FULL = 1, STP_SORT_PPX_KBUFFER = 2, STP_SORT_HIER = 3 };
@@ -128,9 +128,10 @@ int stp_forward(stp_alloc_fn geom_alloc, void* geom_user,
 
 /* replaces: CudaRasterizer::Rasterizer::backward, rasterizer.h:222-257 (impl rasterizer_impl.cu:417-526)
  * as called by RasterizeGaussiansBackwardCUDA, rasterize_points.cu:141-232.
- * grad_accum [P,12] f32 is the only buffer the caller must zero-fill: the render-backward kernels accumulate the
- * screen-space gradients there, packed for 128-bit vector reductions ({conic.x, conic.y, conic.w, opacity | mean2D.x,
- * mean2D.y, color.r, color.g | color.b}; the reference zero-fills nine separate tensors, rasterize_points.cu:178-186).
+ * grad_accum (9 P floats) is the only buffer the caller must zero-fill: the render-backward kernels accumulate the
+ * screen-space gradients there, packed for 128-bit vector reductions in three planes (A [P][4]: conic.x, conic.y, conic.w,
+ * opacity; B [P][4]: mean2D.x, mean2D.y, color.r, color.g; C [P]: color.b; the reference zero-fills nine separate tensors,
+ * rasterize_points.cu:178-186).  It is also what a tile-sharded run all-reduces (36 B per Gaussian).
  * grad_accum and dL_drot must be 16-byte aligned (128-bit reductions / stores); shs and dL_dsh take a faster path
  * when they are.  All dL_* arrays are pure outputs and may be uninitialised -- every row is written, zeros for culled
  * Gaussians:

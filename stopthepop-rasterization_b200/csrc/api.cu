@@ -601,6 +601,7 @@ int backward_impl(int which, int first, int count, int P, int D, int M, size_t b
         ra.pixel_colors = pixel_colors;
         ra.dL_dpix = dL_dpix;
         ra.grad_accum = grad_accum;
+        ra.P = P;
         ra.blend_rec = img.blend_rec;
         ra.blend_count = img.blend_count;
         ra.tile_flags = img.tile_flags;
@@ -633,7 +634,7 @@ int backward_impl(int which, int first, int count, int P, int D, int M, size_t b
         PreprocessBwdArgs pa;
         pa.P = P; pa.D = D; pa.M = M;
         pa.first = first; pa.P_end = first + count;
-        pa.means3D = means3D; pa.radii = radii; pa.shs = shs; pa.clamped = g.clamped; pa.opacities = opacities;
+        pa.means3D = means3D; pa.radii = radii; pa.shs = shs; pa.opacities = opacities;
         pa.scales = scales; pa.rotations = rotations; pa.scale_modifier = scale_modifier;
         pa.cov3D = cov3D_precomp != nullptr ? cov3D_precomp : g.cov3D;
         pa.proper_ewa_scaling = s.proper_ewa_scaling;

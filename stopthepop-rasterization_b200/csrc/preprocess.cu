@@ -16,57 +16,13 @@
 //     kSeqTiles tiles of a rectangle are tested by the owning thread, the remainder by the whole warp.
 //     Results do not depend on the schedule (settings.load_balancing is a no-op by construction).
 #include "stp_kernels.cuh"
+#include "stp_sh.cuh"
 
 namespace stp {
 
 namespace {
 
-constexpr float SH_C0 = 0.28209479177387814f;
-constexpr float SH_C1 = 0.4886025119029199f;
-__constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
-                               -1.0925484305920792f, 0.5462742152960396f};
-__constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
-                               -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
-
 constexpr int kSeqTiles = 8;  // tiles of a rectangle tested sequentially by the owner thread
-
-// SH -> RGB (computeColorFromSH, forward_common.h:20-70); sh points at this Gaussian's
-// coefficients in shared memory, stride 3 floats per coefficient.
-__device__ __forceinline__ void eval_sh(int deg, const float* __restrict__ sh, float dx, float dy, float dz,
-                                        float* __restrict__ rgb, uint8_t* __restrict__ clamped3) {
-    const float len = fsqrt(ffma(dz, dz, ffma(dx, dx, fmul(dy, dy))));
-    const float x = fdiv(dx, len), y = fdiv(dy, len), z = fdiv(dz, len);
-    float r[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) r[c] = SH_C0 * sh[c];
-    if (deg > 0) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) r[c] = r[c] - SH_C1 * y * sh[3 + c] + SH_C1 * z * sh[6 + c] - SH_C1 * x * sh[9 + c];
-        if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                r[c] = r[c] + SH_C2[0] * xy * sh[12 + c] + SH_C2[1] * yz * sh[15 + c] +
-                       SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + SH_C2[3] * xz * sh[21 + c] +
-                       SH_C2[4] * (xx - yy) * sh[24 + c];
-            if (deg > 2) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    r[c] = r[c] + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] + SH_C3[1] * xy * z * sh[30 + c] +
-                           SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
-                           SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
-                           SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] + SH_C3[5] * z * (xx - yy) * sh[42 + c] +
-                           SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
-            }
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        r[c] += 0.5f;
-        clamped3[c] = (r[c] < 0.0f) ? 1 : 0;
-        rgb[c] = fmaxf(r[c], 0.0f);
-    }
-}
 
 // does tile (tx,ty) pass the exact contribution test? (computeTilebasedCullingTileCount,
 // stopthepop_common.cuh:176-262; same arithmetic in duplicateWithKeys_extended :419-452)
@@ -295,7 +251,10 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
     if (a.colors_precomp == nullptr && a.M > 0) {
         const int stride = a.M * 3 + 1;
         float* my_rows = s_sh + (size_t)warp * 32 * stride;
-        uint32_t surv = __ballot_sync(0xffffffffu, alive);
+        // tile band: a Gaussian without an instance in this rank's band is never blended here -- its SH row (81 % of the
+        // bytes this kernel reads) is not fetched and its colour not evaluated
+        const bool coloured = alive && (!BANDED || tiles != 0u);
+        uint32_t surv = __ballot_sync(0xffffffffu, coloured);
         const int warp_base = (int)bid * kPreprocessThreads + warp * 32;
         const int n_sh = a.M * 3;
         const float* __restrict__ wsrc = a.shs + (size_t)warp_base * n_sh;
@@ -314,7 +273,7 @@ preprocess_kernel(PreprocessArgs a, Frame f, GeometryState g, uint32_t* __restri
             }
         }
         __syncwarp();
-        if (alive) {
+        if (coloured) {
             float rgb[3];
             uint8_t cl[3];
             eval_sh(a.D, my_rows + lane * stride, fsub(x, f.cam_pos[0]), fsub(y, f.cam_pos[1]), fsub(z, f.cam_pos[2]),

@@ -8,17 +8,11 @@
 // Gradients are not integer-decision inputs, so this file uses ordinary float expressions
 // (tolerance 1e-5 relative vs. the reference).
 #include "stp_kernels.cuh"
+#include "stp_sh.cuh"
 
 namespace stp {
 
 namespace {
-
-constexpr float SH_C0 = 0.28209479177387814f;
-constexpr float SH_C1 = 0.4886025119029199f;
-__constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
-                               -1.0925484305920792f, 0.5462742152960396f};
-__constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
-                               -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
 
 struct F3 {
     float x, y, z;
@@ -164,9 +158,9 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
 
     // ---------------- conic -> cov2D -> cov3D / mean (computeCov2DCUDA) ----------------
     // packed screen-space gradients of this Gaussian (stp_kernels.cuh: kGradAccum layout)
-    const float4 acc0 = reinterpret_cast<const float4*>(a.grad_accum)[3 * idx];
-    const float4 acc1 = reinterpret_cast<const float4*>(a.grad_accum)[3 * idx + 1];
-    const float acc_cb = a.grad_accum[kGradAccumFloats * idx + 8];
+    const float4 acc0 = reinterpret_cast<const float4*>(a.grad_accum)[idx];                       // plane A
+    const float4 acc1 = reinterpret_cast<const float4*>(a.grad_accum)[(size_t)a.P + idx];          // plane B
+    const float acc_cb = a.grad_accum[8 * (size_t)a.P + idx];                                     // plane C
     const float dcon_x = acc0.x, dcon_y = acc0.y, dcon_z = acc0.z;
     a.dL_dmean2D[3 * idx] = acc1.x;
     a.dL_dmean2D[3 * idx + 1] = acc1.y;
@@ -291,9 +285,16 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreprocessBwdArgs& a, c
         const int D = a.D;
         auto sh = [&](int k) { return F3{shp[3 * k], shp[3 * k + 1], shp[3 * k + 2]}; };
         F3 dRGB = {acc1.z, acc1.w, acc_cb};
-        dRGB.x *= a.clamped[3 * idx + 0] ? 0.f : 1.f;
-        dRGB.y *= a.clamped[3 * idx + 1] ? 0.f : 1.f;
-        dRGB.z *= a.clamped[3 * idx + 2] ? 0.f : 1.f;
+        {
+            // clamp flags of the forward pass (computeColorFromSH sets them where a channel went negative): re-evaluated
+            // with the forward's own function on the same row and direction, before the row is overwritten below
+            float rgb_unused[3];
+            uint8_t cl[3];
+            eval_sh(D, shp, dir_orig.x, dir_orig.y, dir_orig.z, rgb_unused, cl);
+            dRGB.x *= cl[0] ? 0.f : 1.f;
+            dRGB.y *= cl[1] ? 0.f : 1.f;
+            dRGB.z *= cl[2] ? 0.f : 1.f;
+        }
         // weights of dL_dsh[k] = w[k] * dRGB; written after every coefficient has been read (the row is
         // updated in place when it lives in shared memory)
         float wk[16];

@@ -66,11 +66,11 @@ int debug_code(DebugVisualization v) {
     }
 }
 
-// dL_dconic[P,4] = (x, y, -, w) of the packed accumulator (grad_accum[P,12]: floats 0..2)
+// dL_dconic[P,4] = (x, y, -, w) of the packed accumulator (plane A [P][4]: conic.x, conic.y, conic.w, opacity)
 __global__ void unpack_conic_kernel(int P, const float* __restrict__ acc, float* __restrict__ dL_dconic) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    const float4 a = *reinterpret_cast<const float4*>(acc + 12 * (size_t)i);
+    const float4 a = *reinterpret_cast<const float4*>(acc + 4 * (size_t)i);  // plane A of the accumulator
     *reinterpret_cast<float4*>(dL_dconic + 4 * (size_t)i) = make_float4(a.x, a.y, 0.f, a.z);
 }
 
@@ -173,8 +173,8 @@ void Rasterizer::backward(const int P, int D, int M, int /*R*/, const float* bac
         binning_bytes = it->second;
     }
     float* accum = nullptr;  // the packed screen-space accumulator of the C ABI (the reference zero-fills nine arrays)
-    if (cudaMalloc(&accum, sizeof(float) * 12 * (size_t)P) != cudaSuccess) throw std::runtime_error("cudaMalloc(grad_accum) failed");
-    cudaMemsetAsync(accum, 0, sizeof(float) * 12 * (size_t)P, nullptr);
+    if (cudaMalloc(&accum, sizeof(float) * 9 * (size_t)P) != cudaSuccess) throw std::runtime_error("cudaMalloc(grad_accum) failed");
+    cudaMemsetAsync(accum, 0, sizeof(float) * 9 * (size_t)P, nullptr);
     const int rc = stp_backward(P, D, M, binning_bytes, background, width, height, &s, nullptr, means3D, shs, opacities,
                                 colors_precomp, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
                                 inv_viewprojmatrix, cam_pos, tan_fovx, tan_fovy, pixel_colors, radii, geom_buffer, binning_buffer,

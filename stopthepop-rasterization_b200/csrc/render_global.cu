@@ -325,10 +325,10 @@ render_global_bwd_kernel(Frame f, RenderBwdArgs a) {
             const float m0 = s_acc[tid][3], m1 = s_acc[tid][4];
             const float k0 = s_acc[tid][5], k1 = s_acc[tid][6], k2 = s_acc[tid][7];
             const float o = s_acc[tid][8];
-            float* const acc = a.grad_accum + (size_t)kGradAccumFloats * id;
-            if (k0 != 0.f || k1 != 0.f || k2 != 0.f || o != 0.f) red_add_v4(acc, k0, k1, k2, o);
-            if (m0 != 0.f || m1 != 0.f || c0 != 0.f || c1 != 0.f) red_add_v4(acc + 4, m0, m1, c0, c1);
-            if (c2 != 0.f) atomicAdd(acc + 8, c2);
+            float* const acc = a.grad_accum;
+            if (k0 != 0.f || k1 != 0.f || k2 != 0.f || o != 0.f) red_add_v4(acc + 4 * (size_t)id, k0, k1, k2, o);
+            if (m0 != 0.f || m1 != 0.f || c0 != 0.f || c1 != 0.f) red_add_v4(acc + 4 * ((size_t)a.P + id), m0, m1, c0, c1);
+            if (c2 != 0.f) atomicAdd(acc + 8 * (size_t)a.P + id, c2);
         }
     }
 }

@@ -135,7 +135,7 @@ render_kbuffer_kernel(Frame f, RenderArgs a, RenderBwdArgs ab) {
             const float gdx = G * dx, gdy = G * dy;
             const float dG_ddelx = -gdx * co.x - gdy * co.y;
             const float dG_ddely = -gdy * co.z - gdx * co.y;
-            accumulate_grads(ab.grad_accum, id, dchannel_dcolor * g0, dchannel_dcolor * g1, dchannel_dcolor * g2,
+            accumulate_grads(ab.grad_accum, ab.P, id, dchannel_dcolor * g0, dchannel_dcolor * g1, dchannel_dcolor * g2,
                              dL_dG * dG_ddelx * ddelx_dx, dL_dG * dG_ddely * ddely_dy, -0.5f * gdx * dx * dL_dG,
                              -0.5f * gdx * dy * dL_dG, -0.5f * gdy * dy * dL_dG, G * dL_dalpha);
             T = test_T;

@@ -57,7 +57,8 @@ struct RenderBwdArgs {
     const uint32_t* n_contrib;
     const float* pixel_colors;
     const float* dL_dpix;
-    float* grad_accum;   // [P,12] packed screen-space gradient accumulator (kGradAccum*, zero-filled by the caller)
+    float* grad_accum;   // packed screen-space gradient accumulator, 9 P floats in three planes (zero-filled by the caller)
+    int P;               // number of Gaussians (plane stride of the accumulator)
     const uint2* blend_rec;  // blend log written by the forward pass (nullptr = list-driven backward for everything)
     const uint32_t* blend_count;
     const uint32_t* tile_flags;
@@ -70,14 +71,13 @@ struct PreprocessBwdArgs {
     const float* means3D;
     const int* radii;
     const float* shs;
-    const uint8_t* clamped;
     const float* opacities;
     const float* scales;
     const float* rotations;
     float scale_modifier;
     const float* cov3D;  // precomputed or geometry-state cov3D
     bool proper_ewa_scaling;
-    const float* grad_accum;  // [P,12] filled by the render-backward kernels
+    const float* grad_accum;  // 9 P floats in three planes, filled by the render-backward kernels
     float* dL_dmean2D;        // [P,3] out (z = 0)
     float* dL_dopacity;       // [P]   out
     float* dL_dmean3D;
@@ -88,23 +88,23 @@ struct PreprocessBwdArgs {
     float* dL_drot;
 };
 
-// Packed per-Gaussian accumulator of the screen-space gradients, 12 floats = three 16-byte groups
-//   [0..3] dL_dconic.x, dL_dconic.y, dL_dconic.w, dL_dopacity   [4..7] dL_dmean2D.x, dL_dmean2D.y, dL_dcolor.r, dL_dcolor.g
-//   [8] dL_dcolor.b
+// Packed accumulator of the screen-space gradients: nine floats per Gaussian in three PLANES
+//   A [P][4]: dL_dconic.x, dL_dconic.y, dL_dconic.w, dL_dopacity     B [P][4]: dL_dmean2D.x, dL_dmean2D.y, dL_dcolor.r, .g
+//   C [P]   : dL_dcolor.b
 // so that one blend costs two 128-bit vector reductions (REDG.E.ADD.F32x4, sm_90+) and one scalar reduction instead of
 // the reference's nine scalar float atomics (backward.cu:561,583-592): the render-backward kernels are bound by the
-// number of reduction requests the SM can issue, not by the bytes.
-constexpr int kGradAccumFloats = 12;
+// number of reduction requests the SM can issue, not by the bytes.  Planes instead of 48-byte rows: every float of the
+// buffer is used, so a tile-sharded run all-reduces 36 B per Gaussian, not 48.
+constexpr int kGradAccumFloats = 9;
 #ifdef __CUDACC__
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void accumulate_grads(float* __restrict__ acc, int id, float col0, float col1, float col2, float m0,
-                                                 float m1, float k0, float k1, float k2, float op) {
-    float* p = acc + (size_t)kGradAccumFloats * id;
-    red_add_v4(p, k0, k1, k2, op);
-    red_add_v4(p + 4, m0, m1, col0, col1);
-    atomicAdd(p + 8, col2);
+__device__ __forceinline__ void accumulate_grads(float* __restrict__ acc, int P, int id, float col0, float col1, float col2,
+                                                 float m0, float m1, float k0, float k1, float k2, float op) {
+    red_add_v4(acc + 4 * (size_t)id, k0, k1, k2, op);
+    red_add_v4(acc + 4 * ((size_t)P + id), m0, m1, col0, col1);
+    atomicAdd(acc + 8 * (size_t)P + id, col2);
 }
 #endif
 

@@ -107,7 +107,7 @@ _lib.stp_backward_render.argtypes = list(_lib.stp_backward.argtypes)
 _lib.stp_backward_preprocess.restype = ctypes.c_int
 _lib.stp_backward_preprocess.argtypes = list(_lib.stp_backward.argtypes) + [ctypes.c_int, ctypes.c_int]
 
-if _lib.stp_abi_version() != 6:
+if _lib.stp_abi_version() != 7:
     raise ImportError("libstp_rasterizer.so ABI version mismatch")
 
 LIBRARY_PATH = _LIB_PATH
@@ -385,7 +385,7 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
     parameter-gradient slab; with sync_chunks > 1 overlapped with the computation: the preprocess-backward stage runs in
     `sync_chunks` ranges of Gaussians and the all-reduce of each range's SH-gradient rows (81 % of the bytes) starts on a
     side stream as soon as the range is done (measured slower on NVSwitch, see VIEW_SYNC_CHUNKS).
-    Tile bands (tile_band given): the packed screen-space accumulator (48 B/Gaussian) is all-reduced between the two
+    Tile bands (tile_band given): the packed screen-space accumulator (36 B/Gaussian) is all-reduced between the two
     backward stages instead (_backward_band_exchange); all eight returned gradients are then the full-frame ones."""
     if sync_chunks is None:
         sync_chunks = VIEW_SYNC_CHUNKS
@@ -399,14 +399,14 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
     M = sh.size(1) if sh is not None and sh.numel() != 0 else 0
     st = settings_from_dict(settings_dict, blend_record_cap_of(imageBuffer, W, H))
     # ONE slab instead of nine torch::zeros (rasterize_points.cu:178-186).  Only the packed screen-space accumulator
-    # (48 B/Gaussian, include/stp_rasterizer.h) is cleared; every row of the eight outputs is written by the
+    # (36 B/Gaussian, include/stp_rasterizer.h) is cleared; every row of the eight outputs is written by the
     # preprocess-backward kernel (zeros for culled Gaussians).  The five PARAMETER gradients come first and
     # contiguous, so a data-parallel caller can all-reduce them as one buffer (stp_sharding.py); the per-view
     # intermediates follow.
-    widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 12]  # sh means3D scales rot opacity | means2D colors cov3D | accumulator
+    widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 9]  # sh means3D scales rot opacity | means2D colors cov3D | accumulator
     offs = slab_offsets(P, M)  # every sub-array starts on a 16-byte boundary (128-bit stores / vector reductions)
     flat = torch.empty((offs[-1],), dtype=torch.float32, device=device)
-    flat[offs[8]:offs[8] + 12 * P].zero_()
+    flat[offs[8]:offs[8] + 9 * P].zero_()
     views = [flat[offs[i]:offs[i] + widths[i] * P] for i in range(9)]
     dL_dsh, dL_dmeans3D, dL_dscales, dL_drot, dL_dopacity, dL_dmeans2D, dL_dcolors, dL_dcov3D, grad_accum = views
     param_slab = flat[:offs[5]]
@@ -451,7 +451,7 @@ def rasterize_gaussians_backward(background, means3D, radii, opacities, colors, 
 def slab_offsets(P, M):
     """float offsets of the nine sub-arrays of the backward slab (sh, means3D, scales, rot, opacity | means2D, colors,
     cov3D | accumulator) and its total length; each start is rounded up to a multiple of 4 floats."""
-    widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 12]
+    widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 9]
     offs, off = [], 0
     for w in widths:
         off = (off + 3) // 4 * 4
@@ -508,8 +508,8 @@ BAND_SYNC_CHUNKS = int(os.environ.get("STP_BAND_SYNC_CHUNKS", "1"))
 def _backward_band_exchange(args, P, grad_accum, group, device, chunks=1):
     """tile-band sharding (one view, bands of tile rows per rank): the per-Gaussian backward is linear in the packed
     screen-space gradients, and every rank holds the geometry state of every visible Gaussian (visibility does not
-    depend on the band, preprocess.cu), so the ONE exchange is an all-reduce of the 48 B/Gaussian accumulator between
-    the render-backward and the preprocess-backward stage -- 5x less than the 236 B/Gaussian of parameter gradients
+    depend on the band, preprocess.cu), so the ONE exchange is an all-reduce of the 36 B/Gaussian accumulator between
+    the render-backward and the preprocess-backward stage -- 6.5x less than the 236 B/Gaussian of parameter gradients
      -- after which every rank finishes the same preprocess-backward and holds the full gradients.
     The accumulator can be reduced in `chunks` ranges of Gaussians on a side stream, the preprocess-backward of a range
     starting as soon as its sum has arrived; the default is ONE all-reduce (see BAND_SYNC_CHUNKS)."""
@@ -527,7 +527,11 @@ def _backward_band_exchange(args, P, grad_accum, group, device, chunks=1):
     with torch.cuda.stream(comm):
         for first in range(0, P, step):
             count = min(step, P - first)
-            dist.all_reduce(grad_accum[first * 12:(first + count) * 12], group=group)
+            if first == 0 and count == P:
+                dist.all_reduce(grad_accum, group=group)  # 9 P floats, every one of them used
+            else:  # the three planes of the range
+                for base, width in ((0, 4), (4 * P, 4), (8 * P, 1)):
+                    dist.all_reduce(grad_accum[base + first * width:base + (first + count) * width], group=group)
             ev = torch.cuda.Event()
             ev.record(comm)
             ranges.append((first, count))

@@ -101,7 +101,7 @@ def test_backward_slab_layout_is_aligned_and_matches_sharding_helper():
     from diff_gaussian_rasterization import _C
     for P, M in ((1, 16), (3, 16), (7, 4), (1025, 1), (6001, 9), (4096, 16), (5, 0)):
         offs = _C.slab_offsets(P, M)
-        widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 12]
+        widths = [3 * M, 3, 3, 4, 1, 3, 3, 6, 9]
         assert all(o % 4 == 0 for o in offs)
         assert all(offs[i] + widths[i] * P <= offs[i + 1] for i in range(9))
         assert offs[5] == sh.param_slab_numel(P, M)
