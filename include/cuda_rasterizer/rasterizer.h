@@ -74,63 +74,74 @@ struct SplattingSettings {
 };
 
 #ifdef NLOHMANN_JSON_VERSION_MAJOR
-/* same schema as the reference (every key mandatory on input) */
+/* JSON schema of the settings files (same keys as the reference; every key mandatory on input).  One visitor lists the
+ * leaves; to_json writes them, from_json reads them with .at(), i.e. a missing key throws. */
+namespace detail {
+template <class Settings, class Leaf>
+inline void visit_settings(Settings& s, Leaf leaf) {
+    leaf("sort_settings", nullptr, "sort_mode", s.sort_settings.sort_mode);
+    leaf("sort_settings", nullptr, "sort_order", s.sort_settings.sort_order);
+    leaf("sort_settings", "queue_sizes", "tile_4x4", s.sort_settings.queue_sizes.tile_4x4);
+    leaf("sort_settings", "queue_sizes", "tile_2x2", s.sort_settings.queue_sizes.tile_2x2);
+    leaf("sort_settings", "queue_sizes", "per_pixel", s.sort_settings.queue_sizes.per_pixel);
+    leaf("culling_settings", nullptr, "rect_bounding", s.culling_settings.rect_bounding);
+    leaf("culling_settings", nullptr, "tight_opacity_bounding", s.culling_settings.tight_opacity_bounding);
+    leaf("culling_settings", nullptr, "tile_based_culling", s.culling_settings.tile_based_culling);
+    leaf("culling_settings", nullptr, "hierarchical_4x4_culling", s.culling_settings.hierarchical_4x4_culling);
+    leaf(nullptr, nullptr, "load_balancing", s.load_balancing);
+    leaf(nullptr, nullptr, "proper_ewa_scaling", s.proper_ewa_scaling);
+}
+}  // namespace detail
 inline void to_json(nlohmann::json& j, const SplattingSettings& s) {
-    const SortSettings& ss = s.sort_settings;
-    const CullingSettings& cs = s.culling_settings;
-    j = nlohmann::json{
-        {"sort_settings",
-         {{"sort_mode", ss.sort_mode},
-          {"sort_order", ss.sort_order},
-          {"queue_sizes", {{"tile_4x4", ss.queue_sizes.tile_4x4}, {"tile_2x2", ss.queue_sizes.tile_2x2}, {"per_pixel", ss.queue_sizes.per_pixel}}}}},
-        {"culling_settings",
-         {{"rect_bounding", cs.rect_bounding},
-          {"tight_opacity_bounding", cs.tight_opacity_bounding},
-          {"tile_based_culling", cs.tile_based_culling},
-          {"hierarchical_4x4_culling", cs.hierarchical_4x4_culling}}},
-        {"load_balancing", s.load_balancing},
-        {"proper_ewa_scaling", s.proper_ewa_scaling}};
+    j = nlohmann::json::object();
+    detail::visit_settings(s, [&j](const char* group, const char* sub, const char* key, const auto& value) {
+        nlohmann::json* node = &j;
+        if (group) node = &(*node)[group];
+        if (sub) node = &(*node)[sub];
+        (*node)[key] = value;
+    });
 }
 inline void from_json(const nlohmann::json& j, SplattingSettings& s) {
-    const nlohmann::json& so = j.at("sort_settings");
-    so.at("sort_mode").get_to(s.sort_settings.sort_mode);
-    so.at("sort_order").get_to(s.sort_settings.sort_order);
-    const nlohmann::json& q = so.at("queue_sizes");
-    q.at("tile_4x4").get_to(s.sort_settings.queue_sizes.tile_4x4);
-    q.at("tile_2x2").get_to(s.sort_settings.queue_sizes.tile_2x2);
-    q.at("per_pixel").get_to(s.sort_settings.queue_sizes.per_pixel);
-    const nlohmann::json& c = j.at("culling_settings");
-    c.at("rect_bounding").get_to(s.culling_settings.rect_bounding);
-    c.at("tight_opacity_bounding").get_to(s.culling_settings.tight_opacity_bounding);
-    c.at("tile_based_culling").get_to(s.culling_settings.tile_based_culling);
-    c.at("hierarchical_4x4_culling").get_to(s.culling_settings.hierarchical_4x4_culling);
-    j.at("load_balancing").get_to(s.load_balancing);
-    j.at("proper_ewa_scaling").get_to(s.proper_ewa_scaling);
+    detail::visit_settings(s, [&j](const char* group, const char* sub, const char* key, auto& value) {
+        const nlohmann::json* node = &j;
+        if (group) node = &node->at(group);
+        if (sub) node = &node->at(sub);
+        node->at(key).get_to(value);
+    });
 }
 #endif
 
 class Rasterizer {
 public:
+    /* present[i] = Gaussian i passes the near-plane test of the frustum */
     static void markVisible(int P, float* means3D, float* viewmatrix, float* projmatrix, bool* present);
 
+    /* returns num_rendered; the three arenas are requested through the callbacks (device memory, kept by the caller) */
     static int forward(std::function<char*(size_t)> geometryBuffer, std::function<char*(size_t)> binningBuffer,
-                       std::function<char*(size_t)> imageBuffer, const int P, int D, int M, const float* background,
-                       const int width, int height, const SplattingSettings splatting_settings,
-                       DebugVisualizationData& debugVisualization, const float* means3D, const float* shs,
-                       const float* colors_precomp, const float* opacities, const float* scales, const float scale_modifier,
-                       const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
-                       const float* inv_viewprojmatrix, const float* cam_pos, const float tan_fovx, float tan_fovy,
-                       const bool prefiltered, float* out_color, int* radii = nullptr, bool debug = false);
+                       std::function<char*(size_t)> imageBuffer,
+                       const int P, int D, int M,
+                       const float* background, const int width, int height,
+                       const SplattingSettings splatting_settings, DebugVisualizationData& debugVisualization,
+                       const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+                       const float* scales, const float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                       const float* viewmatrix, const float* projmatrix, const float* inv_viewprojmatrix, const float* cam_pos,
+                       const float tan_fovx, float tan_fovy, const bool prefiltered,
+                       float* out_color, int* radii = nullptr, bool debug = false);
 
-    static void backward(const int P, int D, int M, int R, const float* background, const int width, int height,
+    /* gradients of everything forward() consumed; the geometry / binning / image arenas are the ones forward() filled */
+    static void backward(const int P, int D, int M, int R,
+                         const float* background, const int width, int height,
                          const SortSettings sort_settings, const CullingSettings culling_settings, const bool proper_ewa_scaling,
                          const float* means3D, const float* shs, const float* opacities, const float* colors_precomp,
                          const float* scales, const float scale_modifier, const float* rotations, const float* cov3D_precomp,
                          const float* viewmatrix, const float* projmatrix, const float* inv_viewprojmatrix, const float* cam_pos,
-                         const float tan_fovx, float tan_fovy, const float* pixel_colors, const int* radii, char* geom_buffer,
-                         char* binning_buffer, char* image_buffer, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
-                         float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
-                         float* dL_dscale, float* dL_drot, bool debug);
+                         const float tan_fovx, float tan_fovy,
+                         const float* pixel_colors, const int* radii,
+                         char* geom_buffer, char* binning_buffer, char* image_buffer,
+                         const float* dL_dpix,
+                         float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
+                         float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                         bool debug);
 };
 
 }  // namespace CudaRasterizer

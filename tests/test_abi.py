@@ -135,3 +135,26 @@ def test_settings_struct_is_the_same_in_header_binding_and_integration_doc():
     doc_fields = re.findall(r'"([a-z_0-9A-Z]+)"', stub)
     assert doc_fields == [n for n, _ in fields]
     assert f"stp_abi_version() == {_C._lib.stp_abi_version()}" in doc
+
+
+def test_cpp_settings_json_converters_roundtrip(tmp_path):
+    """to_json / from_json of CudaRasterizer::SplattingSettings (the reference's rasterizer.h:137-182, used by the viewer to
+    load the StopThePop preset files): same keys, missing key -> exception.  Needs some nlohmann/json on the machine."""
+    import glob
+    import shutil
+    import subprocess
+    import sysconfig
+    cands = glob.glob(os.path.join(sysconfig.get_paths()["purelib"], "include", "**", "nlohmann", "json.hpp"), recursive=True)
+    cands += glob.glob("/usr/include/nlohmann/json.hpp")
+    if not cands or shutil.which("g++") is None:
+        pytest.skip("nlohmann/json.hpp or g++ not available")
+    inc = os.path.dirname(os.path.dirname(cands[0]))
+    exe = tmp_path / "json_rt"
+    subprocess.check_call(["g++", "-std=c++17", "-I" + inc, "-I" + os.path.join(ROOT, "include", "cuda_rasterizer"),
+                           os.path.join(ROOT, "tests", "cpp", "settings_json_roundtrip.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    import json
+    d = json.loads(out.stdout.strip().splitlines()[0])
+    assert d["sort_settings"]["queue_sizes"] == {"per_pixel": 8, "tile_2x2": 8, "tile_4x4": 64}
+    assert set(d) == {"sort_settings", "culling_settings", "load_balancing", "proper_ewa_scaling"}
