@@ -55,6 +55,8 @@ def lib():
         _lib.orc_forward.argtypes = [ctypes.POINTER(OrcInputs), ctypes.POINTER(OrcSettings)]
         _lib.orc_backward.restype = ctypes.c_int
         _lib.orc_free.argtypes = [ctypes.POINTER(OrcState)]
+        _lib.orc_debug_visualisation.restype = ctypes.POINTER(OrcState)
+        _lib.orc_debug_visualisation.argtypes = [ctypes.POINTER(OrcInputs), ctypes.POINTER(OrcSettings), ctypes.c_int, _fp]
     return _lib
 
 
@@ -68,6 +70,60 @@ def settings_struct(d):
 
 def _c(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+# DebugVisualization codes of include/stp_rasterizer.h (STP_DEBUG_*)
+SORT_ERROR_OPACITY, SORT_ERROR_DISTANCE, COUNT_PER_TILE, DEPTH, COUNT_PER_PIXEL, TRANSMITTANCE = 1, 2, 3, 4, 5, 6
+
+# Magma: degree-6 polynomial per channel, M. Zucker's public-domain fit of matplotlib's table -- the coefficients the
+# reference evaluates in colormapMagma (stopthepop_common.cuh:623-642)
+_MAGMA = np.array([[-0.002136485053939582, -0.000749655052795221, -0.005386127855323933],
+                   [0.2516605407371642, 0.6775232436837668, 2.494026599312351],
+                   [8.353717279216625, -3.577719514958484, 0.3144679030132573],
+                   [-27.66873308576866, 14.26473078096533, -13.64921318813922],
+                   [52.17613981234068, -27.94360607168351, 12.94416944238394],
+                   [-50.76852536473588, 29.04658282127291, 4.23415299384598],
+                   [18.65570506591883, -11.48977351997711, -5.601961508734096]], dtype=np.float32)
+_turbo = None
+
+
+def turbo_table():
+    """Google's published 256-entry Turbo sRGB table (A. Mikhailov 2019, Apache-2.0), which the reference embeds in
+    colormapTurbo (stopthepop_common.cuh:645-656).  Read from the one copy of the table in this repository; the golden
+    render_depth images of the reference build (tests/golden/depth_vis_*.npz) pin it."""
+    global _turbo
+    if _turbo is None:
+        import re
+        path = os.path.join(_HERE, "..", "stopthepop-rasterization_b200", "csrc", "stp_turbo_lut.cuh")
+        body = open(path).read().split("kTurboLut[256][3]", 1)[1]
+        vals = [float(x) for x in re.findall(r"(\d\.\d+)f", body)]
+        assert len(vals) == 768
+        _turbo = np.array(vals, dtype=np.float32).reshape(256, 3)
+    return _turbo
+
+
+def colormap(value, T, kind, debug_range=None):
+    """render_debug_CUDA, forward.cu:674-714: value / T [H,W] float32 -> [3,H,W].  Depth: Turbo of
+    clamp(value + T * max, min, max) / (max - min); the others: Magma of clamp(value, min, max) / (max - min), with
+    (min, max) of the value plane (applyDebugVisualization, rasterizer_impl.cu:66-76) or the caller's (debug_normalize)."""
+    f = np.float32
+    mn, mx = (f(value.min()), f(value.max())) if debug_range is None else (f(debug_range[0]), f(debug_range[1]))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if kind == DEPTH:
+            x = np.minimum(np.maximum(value + T * mx, mn), mx) / f(mx - mn)
+            interp = np.minimum(np.maximum(x * f(255.0), f(0.0)), f(255.0))
+            lo = np.where(x > 0, interp.astype(np.int32), 0)
+            hi = np.where(lo >= 255, 255, lo + 1)
+            diff = (interp - lo.astype(f))[..., None]
+            lut = turbo_table()
+            rgb = np.clip(lut[lo] + (lut[hi] - lut[lo]) * diff, f(0), f(1))
+        else:
+            x = np.clip(np.minimum(np.maximum(value, mn), mx) / f(mx - mn), f(0), f(1))[..., None]
+            rgb = np.broadcast_to(_MAGMA[6], x.shape[:-1] + (3,)).astype(f)
+            for k in range(5, -1, -1):
+                rgb = _MAGMA[k] + x * rgb
+            rgb = np.clip(rgb, f(0), f(1))
+    return np.ascontiguousarray(np.moveaxis(rgb.astype(f), -1, 0))
 
 
 def _p(a):
@@ -129,6 +185,18 @@ class Oracle:
             raise RuntimeError("Backward not supported for full per-pixel sort")
         g["dL_dsh"] = g["dL_dsh"][:, :M]
         return g
+
+    def debug_visualisation(self, kind, debug_range=None):
+        """The ENABLE_DEBUG_VIZ forward pass (accumSortingErrorDepth / outputDebugVis, stopthepop_common.cuh:264-307) of
+        this scene: returns dict(value[H,W], T[H,W], stats=(min, max, mean, std) of value as the viewer's callback gets
+        them (rasterizer_impl.cu:66-97), image[3,H,W] = the colour-mapped frame)."""
+        raw = np.zeros((2, self.H * self.W), dtype=np.float32)
+        st = lib().orc_debug_visualisation(ctypes.byref(self.inp), ctypes.byref(self.settings), int(kind), _p(raw))
+        lib().orc_free(st)
+        value, T = raw[0].reshape(self.H, self.W), raw[1].reshape(self.H, self.W)
+        v64 = value.astype(np.float64)
+        stats = (float(value.min()), float(value.max()), float(v64.mean()), float(v64.std()))
+        return dict(value=value, T=T, stats=stats, image=colormap(value, T, int(kind), debug_range))
 
     def close(self):
         if self.st:

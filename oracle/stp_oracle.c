@@ -375,6 +375,43 @@ static void binning(const OrcInputs* in, const OrcSettings* s, OrcState* st) {
 }
 
 /* ---- GLOBAL render, forward.cu:234-366 ------------------------------------------------------------- */
+/* ---- debug visualisation accumulators: accumSortingErrorDepth / outputDebugVis, stopthepop_common.cuh:264-307 ------
+ * The reference compiles each render kernel a second time (ENABLE_DEBUG_VIZ) with these two calls inside the blend loop;
+ * here the four render functions below carry them behind g_vis_type (0 = off, else the STP_DEBUG_* codes of
+ * include/stp_rasterizer.h: 1 SortErrorOpacity, 2 SortErrorDistance, 3 GaussianCountPerTile, 4 Depth,
+ * 5 GaussianCountPerPixel, 6 Transmittance).  orc_debug_visualisation() below returns the raw planes (value, T) that
+ * render_debug_CUDA (forward.cu:674-714) then normalises and colour-maps (oracle/cpu_oracle.py:colormap).
+ * GaussianCountPerPixel: the reference writes its loop counter `contributor` (list entries visited, including the ones
+ * skipped), which depends on the kernel's loop structure; this restatement counts the Gaussians BLENDED, the definition
+ * the CUDA path uses ("Deliberate differences"). */
+static int g_vis_type = 0;
+static float* g_vis_out = NULL; /* [2][H*W] */
+typedef struct { float cur, acc; uint32_t blends; } Vis;
+static void vis_init(Vis* v) { v->cur = -FLT_MAX; v->acc = 0.0f; v->blends = 0; } /* forward.cu:282, hierarchical_render.cuh:983 */
+static void vis_accum(Vis* v, float depth, float alpha, float T) { /* T: transmittance BEFORE this blend */
+    if ((g_vis_type == 1 || g_vis_type == 2) && depth <= v->cur) {
+        if (g_vis_type == 1) v->acc += alpha;
+        else v->acc += fabsf(v->cur - depth);
+    } else if (g_vis_type == 4) {
+        v->acc += depth * alpha * T;
+    }
+    v->cur = fmaxf(v->cur, depth);
+    v->blends++;
+}
+static void vis_store(const OrcInputs* in, const Vis* v, int px, int py, float T, uint32_t range) {
+    if (!g_vis_out || !(px < in->W && py < in->H)) return;
+    const size_t N = (size_t)in->W * in->H, pid = (size_t)py * in->W + px;
+    float out = 0.0f;
+    switch (g_vis_type) {
+        case 1: case 2: case 4: out = v->acc; break;
+        case 3: out = (float)range; break;
+        case 5: out = (float)v->blends; break;
+        case 6: out = 1.0f - T; break;
+    }
+    g_vis_out[pid] = out;
+    g_vis_out[N + pid] = T;
+}
+
 static void render_global(const OrcInputs* in, OrcState* st) {
     const int W = in->W, H = in->H, gx = (W + 15) / 16;
 #pragma omp parallel for schedule(dynamic, 64)
@@ -383,6 +420,7 @@ static void render_global(const OrcInputs* in, OrcState* st) {
         const uint32_t* rg = st->ranges + 2 * ((py / 16) * gx + px / 16);
         float T = 1.0f, C[3] = {0, 0, 0};
         uint32_t contributor = 0, last = 0;
+        Vis vis; vis_init(&vis);
         for (uint32_t j = rg[0]; j < rg[1]; ++j) {
             ++contributor;
             const uint32_t id = st->point_list[j];
@@ -395,9 +433,15 @@ static void render_global(const OrcInputs* in, OrcState* st) {
             const float test_T = T * (1.0f - alpha);
             if (test_T < T_THRESHOLD) break;
             for (int ch = 0; ch < 3; ++ch) C[ch] = fmaf(T, alpha * st->rgb[3 * id + ch], C[ch]);
+            if (g_vis_type) { /* depth = distance of the centre from the camera, forward.cu:337-341 */
+                const float ex = in->campos[0] - in->means3D[3 * id], ey = in->campos[1] - in->means3D[3 * id + 1],
+                            ez = in->campos[2] - in->means3D[3 * id + 2];
+                vis_accum(&vis, sqrtf(ex * ex + ey * ey + ez * ez), alpha, T);
+            }
             T = test_T;
             last = contributor;
         }
+        vis_store(in, &vis, px, py, T, rg[1] - rg[0]);
         st->final_T[pid] = T;
         st->n_contrib[pid] = last;
         for (int ch = 0; ch < 3; ++ch) st->out_color[(size_t)ch * W * H + pid] = fmaf(T, in->bg[ch], C[ch]);
@@ -410,6 +454,7 @@ typedef struct {
     int active;
     /* backward */
     float T_final, g[3], final_color[3];
+    Vis vis;
 } Pix;
 
 typedef struct {
@@ -456,10 +501,11 @@ static int blend_bwd_front_to_back(const OrcInputs* in, const OrcState* st, BwdC
     p->T = test_T;
     return 1;
 }
-static int blend_fwd(const OrcState* st, Pix* p, int id, float alpha) { /* hierarchical_render.cuh:992-1013 */
+static int blend_fwd(const OrcState* st, Pix* p, int id, float alpha, float depth) { /* hierarchical_render.cuh:992-1013 */
     const float test_T = p->T * (1.0f - alpha);
     if (test_T < T_THRESHOLD) return 0;
     for (int ch = 0; ch < 3; ++ch) p->C[ch] += st->rgb[3 * id + ch] * alpha * p->T;
+    if (g_vis_type) vis_accum(&p->vis, depth, alpha, p->T); /* :1005-1008, resorted_render.cuh:105-108 */
     p->T = test_T;
     return 1;
 }
@@ -468,6 +514,7 @@ static void pix_init(const OrcInputs* in, const OrcState* st, const BwdCtx* b, P
     memset(p, 0, sizeof(*p));
     p->T = 1.0f;
     p->active = inside;
+    vis_init(&p->vis);
     if (b && inside) {
         const int pid = py * W + px;
         p->T_final = st->final_T[pid];
@@ -477,10 +524,11 @@ static void pix_init(const OrcInputs* in, const OrcState* st, const BwdCtx* b, P
         }
     }
 }
-static void pix_store(const OrcInputs* in, OrcState* st, const Pix* p, int px, int py, int write_ncontrib, uint32_t nc) {
+static void pix_store(const OrcInputs* in, OrcState* st, const Pix* p, int px, int py, int write_ncontrib, uint32_t nc, uint32_t range) {
     const int W = in->W, H = in->H;
     if (!(px < W && py < H)) return;
     const int pid = py * W + px;
+    vis_store(in, &p->vis, px, py, p->T, range); /* outputDebugVis */
     st->final_T[pid] = p->T;
     if (write_ncontrib) st->n_contrib[pid] = nc;
     for (int ch = 0; ch < 3; ++ch) st->out_color[(size_t)ch * W * H + pid] = p->C[ch] + p->T * in->bg[ch];
@@ -534,7 +582,7 @@ static void head_blend_one(HierCtx* c, HeadQ* q) { /* blend_one, :386-417 */
     int ok;
     const float T_before = q->pix.T;
     if (c->bwd) ok = blend_bwd_front_to_back(c->in, c->st, c->bwd, &q->pix, q->px, q->py, q->h[0].id, q->h[0].store);
-    else ok = blend_fwd(c->st, &q->pix, q->h[0].id, q->h[0].store);
+    else ok = blend_fwd(c->st, &q->pix, q->h[0].id, q->h[0].store, q->h[0].d);
     if (!ok) { q->pix.active = 0; return; }
     if (q->px == g_dbg_px && q->py == g_dbg_py && g_dbg_n < g_dbg_cap) {
         g_dbg_ids[g_dbg_n] = q->h[0].id;
@@ -692,7 +740,7 @@ static void render_hier_block(HierCtx* c, int tile_x, int tile_y, int bx, int by
             while (hq[p].pix.active && hq[p].count > 0) head_blend_one(c, &hq[p]);
     }
     if (!c->bwd)
-        for (int p = 0; p < 16; ++p) pix_store(in, st, &hq[p].pix, hq[p].px, hq[p].py, 0, 0);
+        for (int p = 0; p < 16; ++p) pix_store(in, st, &hq[p].pix, hq[p].px, hq[p].py, 0, 0, r1 - r0);
 }
 static void render_hier(const OrcInputs* in, const OrcSettings* s, OrcState* st, BwdCtx* bwd) {
     const int gx = (in->W + 15) / 16, gy = (in->H + 15) / 16;
@@ -721,7 +769,7 @@ static void render_kbuffer(const OrcInputs* in, const OrcSettings* s, OrcState* 
         for (uint32_t j = rg[0]; j < rg[1] && !done; ++j) {
             if (num == Wn) { /* blend_one */
                 --num;
-                const int ok = bwd ? blend_bwd_front_to_back(in, st, bwd, &p, px, py, q[0].id, q[0].store) : blend_fwd(st, &p, q[0].id, q[0].store);
+                const int ok = bwd ? blend_bwd_front_to_back(in, st, bwd, &p, px, py, q[0].id, q[0].store) : blend_fwd(st, &p, q[0].id, q[0].store, q[0].d);
                 if (!ok) { done = 1; break; }
                 for (int k = 1; k < Wn; ++k) q[k - 1] = q[k];
                 q[Wn - 1].d = FLT_MAX;
@@ -752,12 +800,12 @@ static void render_kbuffer(const OrcInputs* in, const OrcSettings* s, OrcState* 
         if (!done)
             while (num > 0) {
                 --num;
-                const int ok = bwd ? blend_bwd_front_to_back(in, st, bwd, &p, px, py, q[0].id, q[0].store) : blend_fwd(st, &p, q[0].id, q[0].store);
+                const int ok = bwd ? blend_bwd_front_to_back(in, st, bwd, &p, px, py, q[0].id, q[0].store) : blend_fwd(st, &p, q[0].id, q[0].store, q[0].d);
                 if (!ok) break;
                 for (int k = 1; k < Wn; ++k) q[k - 1] = q[k];
                 q[Wn - 1].d = FLT_MAX;
             }
-        if (!bwd) pix_store(in, st, &p, px, py, 1, contributor);
+        if (!bwd) pix_store(in, st, &p, px, py, 1, contributor, rg[1] - rg[0]);
     }
 }
 
@@ -790,6 +838,7 @@ static void render_full(const OrcInputs* in, OrcState* st, BwdCtx* bwd) {
             }
         float T = 1.0f, C[3] = {0, 0, 0}; uint32_t contributor = 0, last = 0; int done = 0, todo = n;
         Pix bp;
+        Vis vis; vis_init(&vis);
         if (bwd) pix_init(in, st, bwd, &bp, px, py);
         for (int r = 0; r < rounds; ++r, todo -= 256) {
             for (int t = 0; t < 256; ++t) {
@@ -823,12 +872,14 @@ static void render_full(const OrcInputs* in, OrcState* st, BwdCtx* bwd) {
                 const float test_T = T * (1.0f - alpha);
                 if (test_T < T_THRESHOLD) { done = 1; continue; }
                 for (int ch = 0; ch < 3; ++ch) C[ch] += st->rgb[3 * id + ch] * alpha * T;
+                if (g_vis_type) vis_accum(&vis, e->k, alpha, T); /* resorted_render.cuh:645-648 */
                 T = test_T;
                 last = contributor;
             }
             memcpy(win, keep, sizeof(keep));
         }
         if (bwd) continue; /* the forward outputs stay as they are */
+        vis_store(in, &vis, px, py, T, (uint32_t)n);
         st->final_T[pid] = T;
         st->n_contrib[pid] = last;
         for (int ch = 0; ch < 3; ++ch) st->out_color[(size_t)ch * W * H + pid] = C[ch] + T * in->bg[ch];
@@ -1042,6 +1093,14 @@ OrcState* orc_forward(const OrcInputs* in, const OrcSettings* s) { /* Rasterizer
         case 2: render_kbuffer(in, s, st, NULL); break;
         default: render_hier(in, s, st, NULL); break;
     }
+    return st;
+}
+/* the ENABLE_DEBUG_VIZ forward pass: raw[0..N) = the visualised quantity, raw[N..2N) = final T (outputDebugVis); the state
+ * of the run (ranges, final_T, ...) is returned like orc_forward's.  Not re-entrant (g_vis_* are process globals). */
+OrcState* orc_debug_visualisation(const OrcInputs* in, const OrcSettings* s, int type, float* raw) {
+    g_vis_type = type; g_vis_out = raw;
+    OrcState* st = orc_forward(in, s);
+    g_vis_type = 0; g_vis_out = NULL;
     return st;
 }
 /* off: mirror the reference (PPX_FULL backward is an error); on: the derived extension of render_full above */

@@ -17,8 +17,10 @@
 //   Transmittance      1 - T_final;   GaussianCountPerTile: length of the tile's list;
 //   GaussianCountPerPixel: Gaussians BLENDED into the pixel (the reference counts the list entries its loop visited,
 //   including the ones it skipped -- a number that depends on its loop structure, not on the image).
-// None of the five non-Depth types can be reached through the reference's Python API, so there is no reference output
-// to pin them against; they are tested through their defining properties (tests/test_gpu_matrix.py).
+// Only Depth can be reached through the reference's Python API.  Its output is compared with the reference build's
+// (tests/test_gpu_parity.py, tests/golden/depth_vis.npz); the other five types are compared with the CPU oracle's
+// restatement of the ENABLE_DEBUG_VIZ kernels, whose accumulators the Depth golden images pin
+// (test_debug_visualisation_matches_cpu_oracle), and through their defining properties (tests/test_gpu_matrix.py).
 #include "stp_kernels.cuh"
 #include "stp_slab.cuh"
 #include "stp_turbo_lut.cuh"

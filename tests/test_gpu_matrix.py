@@ -409,7 +409,8 @@ def _magma(x):
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_debug_visualisations_defining_properties(mode):
     """The five DebugVisualization types besides Depth (rasterizer_debug.h:11-20) cannot be reached through the reference's
-    Python API (render_depth selects Depth only), so they are checked against their definitions:
+    Python API (render_depth selects Depth only).  Next to the comparison with the CPU oracle
+    (test_gpu_parity.py::test_debug_visualisation_matches_cpu_oracle) they are checked against their definitions:
     Transmittance = Magma(1 - final_T); GaussianCountPerTile = Magma(len(tile list) / max); GaussianCountPerPixel: raw
     maximum = the largest blend count; sort errors: exactly zero for the exact per-pixel sort (PPX_FULL, lists <= 1024),
     positive somewhere for the global z-order measured against camera distance."""

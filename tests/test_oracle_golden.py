@@ -217,3 +217,29 @@ def test_oracle_hier_cull_fd_all_parameter_groups(golden):
                 break
         passed[name] = ok
     assert sum(passed.values()) >= 50 and min(passed.values()) >= 5, (passed, worst)
+
+
+DEPTH_VIS_CASES = ["global_default", "global_distance_ewa", "global_tbc_ptdmax", "hier_default", "hier_preset", "hier_q16_20",
+                   "hier_sparse", "hier_long", "kbuffer16", "kbuffer4", "full_sort", "full_sort_long"]
+
+
+@pytest.mark.parametrize("name", DEPTH_VIS_CASES)
+def test_oracle_depth_visualisation_matches_reference_golden(golden, name):
+    """render_depth=True (DebugVisualization::Depth, the one visualisation the reference's Python API reaches,
+    rasterize_points.cu:104-107) of the unmodified reference build on the golden scenes
+    (tests/golden/make_golden_depth_vis.py -> depth_vis.npz) against the oracle's ENABLE_DEBUG_VIZ restatement
+    (stp_oracle.c: vis_accum / vis_store, cpu_oracle.colormap incl. the Turbo table).  This pins the accumulator hook, the
+    per-mode depth (camera distance for GLOBAL, ray depth for the per-pixel modes) and the min/max normalisation that the
+    sort-error visualisations share.  Turbo's slope amplifies differences of the normalised depth by up to ~8 and the
+    min/max of the frame come from single pixels, hence 2e-4 absolute on colours in [0,1]; isolated pixels where an
+    expf ulp flips a threshold decision are bounded by count."""
+    import os
+    from conftest import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, "depth_vis.npz"))[name]
+    f = golden(name)
+    got = f.oracle().debug_visualisation(4)["image"]
+    assert got.shape == ref.shape
+    d = np.abs(got - ref).max(axis=0)
+    bad = int((d > 2e-4).sum())
+    assert bad <= max(1, int(0.002 * d.size)), (bad, float(d.max()))
+    assert float(np.median(d)) <= 2e-5
