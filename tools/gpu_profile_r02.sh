@@ -9,9 +9,9 @@ TAG=${1:-r02prof}; WLS=${2:-"C3b C4 C2"}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 cp profiles/ncu_traffic.json $OUT/ncu_traffic.json 2>/dev/null
 for w in $WLS; do
-  timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+  timeout ${T_LIST:-600} ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
       --log-file $OUT/launches_$w.csv python tools/profile_step.py $w > $OUT/launches_$w.log 2>&1
-  timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -o /tmp/full_$w \
+  timeout ${T_FULL:-900} ncu --profile-from-start off --set full --clock-control none --import-source on -o /tmp/full_$w \
       python tools/profile_step.py $w > $OUT/full_$w.log 2>&1
   python tools/ncu_summary.py /tmp/full_$w.ncu-rep $OUT/ncu_full_summary_$w.csv $w $OUT/ncu_traffic.json > /dev/null 2>&1
   for k in render_hier_kernel blend_replay_bwd render_full_fast render_global_bwd; do
