@@ -268,8 +268,9 @@ def cpu_port_step_seconds(sc_c, cam_c, settings, dL_c, repeats):
 
 def own_sort_bytes(R, T, slab):
     """what the tile-bucket sort of this library moves per launch: 8 B record in, 12 B (key + id) out and, for the
-    depth-resorting modes, the slab record (72 B gathered, 64 B written) -- next to SURVEY 8d's radix-sort formula"""
-    return R * (8 + 12 + (136 if slab else 0)) + 16 * T
+    depth-resorting modes, the slab records (means2D 8 + conic/opacity 16 + inverse covariance 48 + colour 12 B gathered,
+    64 B geometry + 16 B {r,g,b,id} written) -- next to SURVEY 8d's radix-sort formula"""
+    return R * (8 + 12 + (84 + 80 if slab else 0)) + 16 * T
 
 
 def bands_mode_of(workload, sharding, world):
