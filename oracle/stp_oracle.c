@@ -6,7 +6,8 @@
  * call it.  The product (stopthepop-rasterization_b200/) has no CPU path.
  *
  * Parity status: PINNED -- validated against tests/golden/*.npz, which are outputs of the unmodified
- * reference CUDA build (oracle/_ref) run on a B200 (tests/golden/make_golden.py).  The reference
+ * reference CUDA build (oracle/_ref) run on a B200 (tests/golden/make_golden.py; the debug-visualisation
+ * accumulators against its render_depth images, tests/golden/make_golden_depth_vis.py).  The reference
  * itself ships no CPU implementation, tests or golden vectors.
  * Integer outputs (radii, point_list, ranges, n_contrib) are restated exactly; floats differ from
  * the GPU only through libm expf/logf vs. CUDA's (<= 2 ulp), which can flip a threshold decision
